@@ -1,0 +1,141 @@
+/*
+ * ministark_b200.h — C ABI of libministark_b200.so: the B200 (sm_100a) replacement for
+ * the Metal backend of andrewmilson/ministark's `ministark-gpu` crate and for the CPU
+ * steps that sit between its GPU calls in the prover hot path.
+ *
+ * The reference has no FFI of its own (it reaches the device through the `metal`
+ * crate); each entry point below names the reference interface it replaces
+ * (file:line under /root/reference).  A Rust `extern "C"` binding for these symbols is
+ * shown in INTEGRATION.md; include/ministark_gpu.hpp is the C++ mirror of the Rust
+ * item set (GpuFft, GpuIfft, Planner, *Stage, Matrix, MatrixMerkleTree).
+ *
+ * Conventions
+ *   - Field elements are raw 64-bit Montgomery words, canonical (< p), R = 2^64, exactly
+ *     as ark-ff-optimized keeps them in memory (gpu/src/metal/felt_u64.h.metal:118,127).
+ *     MS_FIELD_FP  : 1 word / element.   MS_FIELD_FQ3 : 3 words (c0,c1,c2), X^3 = 2
+ *     (gpu/src/fields.rs:52-53,78-97).
+ *   - A matrix is column-major: column c starts at base + c * col_stride_elems elements
+ *     (src/matrix.rs:26, Vec<GpuVec<F>>).
+ *   - Every pointer argument may be a device pointer, a pinned/managed host pointer or a
+ *     pageable host pointer; host buffers are staged through device scratch inside the
+ *     call (the reference relies on Apple unified memory: gpu/src/utils.rs:106-134).
+ *   - All functions return 0 on success, a negative MS_ERR_* otherwise; the reference
+ *     panics on any failure (gpu/src/stage.rs:55-75, gpu/src/plan.rs:255-257), the
+ *     Rust/C++ shims turn non-zero into panic!/throw.  ms_last_error() gives the text.
+ *   - A context is not re-entrant; all work is issued on its stream in order
+ *     (one in-order Metal queue in the reference, gpu/src/plan.rs:327-350).
+ *   - There is no CPU fallback: without a CUDA device ms_ctx_create fails.
+ */
+#ifndef MINISTARK_B200_H
+#define MINISTARK_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MS_OK 0
+#define MS_ERR_INVALID (-1)   /* bad argument (size not a power of two, out of range, …) */
+#define MS_ERR_CUDA (-2)      /* CUDA runtime failure */
+#define MS_ERR_NOMEM (-3)
+#define MS_ERR_NODEVICE (-4)
+
+#define MS_FIELD_FP 1   /* Goldilocks base field, kernel suffix "p18446744069414584321_fp"  (gpu/src/fields.rs:55-61) */
+#define MS_FIELD_FQ3 3  /* cubic extension,        kernel suffix "p18446744069414584321_fq3" (gpu/src/fields.rs:211-217) */
+
+#define MS_NTT_FORWARD 0 /* FftDirection::Forward (gpu/src/plan.rs:176-183) */
+#define MS_NTT_INVERSE 1 /* FftDirection::Inverse */
+
+/* pointwise stage opcodes (gpu/src/metal/evaluation_shaders.h.metal:11-168) */
+#define MS_OP_MUL 0     /* MulInto / MulAssign                     :58-66,79-88  */
+#define MS_OP_ADD 1     /* AddInto / AddAssign                     :68-76,90-99  */
+#define MS_OP_CONVERT 2 /* ConvertInto (Fp -> Fq3 embed)           :121-127      */
+#define MS_OP_INV 3     /* InverseInto / InverseInPlace            :11-16,33-39  */
+#define MS_OP_EXP 4     /* ExpInto / ExpInPlace                    :18-24,41-48  */
+#define MS_OP_NEG 5     /* NegInto / NegInPlace                    :26-31,50-56  */
+#define MS_OP_MULPOW 6  /* MulPow                                  :149-161      */
+#define MS_OP_FILL 7    /* FillBuff                                :163-168      */
+#define MS_OP_SUB 8     /* (not a reference stage; used by the fused evaluator) */
+
+typedef struct ms_ctx ms_ctx;
+typedef struct ms_ntt_plan ms_ntt_plan;
+
+/* ---- context: replaces Planner / get_planner() (gpu/src/plan.rs:327-350,465-469) ---- */
+int ms_ctx_create(int device, ms_ctx **out);
+int ms_ctx_destroy(ms_ctx *ctx);
+/* use an existing cudaStream_t (e.g. torch's current stream); NULL = the context's own */
+int ms_ctx_set_stream(ms_ctx *ctx, void *cuda_stream);
+int ms_ctx_sync(ms_ctx *ctx);
+const char *ms_last_error(ms_ctx *ctx);
+const char *ms_version(void);
+/* number of kernels this context has launched so far (bench.py "gpu_launches") */
+uint64_t ms_launch_count(ms_ctx *ctx);
+
+/* ---- memory: backs GpuAllocator / GpuVec (src/utils.rs:438-493) and
+ *      page_aligned_uninit_vector (gpu/src/utils.rs:208-220) ---- */
+int ms_alloc_device(ms_ctx *ctx, size_t bytes, void **out);
+int ms_alloc_host_pinned(ms_ctx *ctx, size_t bytes, void **out);
+int ms_free(ms_ctx *ctx, void *ptr); /* either kind */
+int ms_copy(ms_ctx *ctx, void *dst, const void *src, size_t bytes); /* any direction, stream-ordered + sync */
+
+/* ---- GpuFft / GpuIfft (gpu/src/plan.rs:236-325): plan, encode many columns, execute ----
+ * log_n in [0, 32].  offset_mont = domain.offset as a Montgomery word (ONE = 4294967295
+ * for a subgroup).  Forward: out[i] = sum_j c_j (offset*g^i)^j, natural order in place.
+ * Inverse: the inverse map incl. 1/n and offset^-j (gpu/src/plan.rs:404-424).
+ * GpuFft::MIN_SIZE (2048, plan.rs:246) is NOT enforced: smaller sizes also run on device. */
+int ms_ntt_plan_create(ms_ctx *ctx, int field, unsigned log_n, int direction, uint64_t offset_mont,
+                       ms_ntt_plan **out);
+int ms_ntt_encode(ms_ntt_plan *plan, void *column);   /* exactly 2^log_n elements, transformed in place */
+int ms_ntt_execute(ms_ntt_plan *plan);                /* runs everything encoded; blocks; clears the queue */
+int ms_ntt_plan_destroy(ms_ntt_plan *plan);
+
+/* ---- resident batched forms used by Matrix::{into_polynomials,into_evaluations,
+ *      into_bit_reversed_evaluations} (src/matrix.rs:101-251) ---- */
+int ms_ntt_batch(ms_ctx *ctx, int field, void *data, size_t col_stride_elems, unsigned ncols,
+                 unsigned log_n, int direction, uint64_t offset_mont);
+/* coefficients (2^log_n per column) -> evaluations over offset*<g_N>, N = 2^(log_n+log_blowup),
+ * bit-reversed row order when bitrev_out != 0 (no zero padding, no separate bit-reverse pass). */
+int ms_lde_batch(ms_ctx *ctx, int field, const void *coeffs, size_t in_stride_elems, void *evals,
+                 size_t out_stride_elems, unsigned ncols, unsigned log_n, unsigned log_blowup,
+                 uint64_t offset_mont, int bitrev_out);
+
+/* ---- bit_reverse (gpu/src/utils.rs:32-78, BitReverseGpuStage stage.rs:280-332) ---- */
+int ms_bit_reverse(ms_ctx *ctx, int field, void *data, size_t col_stride_elems, unsigned ncols, unsigned log_n);
+
+/* ---- pointwise stages (gpu/src/stage.rs, 14 stage types; evaluation_shaders.h.metal) ----
+ * dst[i] = lhs[i] OP rhs[(i + shift) % n].  dst may alias lhs (the *Assign/*InPlace forms).
+ * Unary ops (INV, EXP, NEG, CONVERT) ignore rhs.  exponent is used by EXP / MULPOW. */
+int ms_pointwise(ms_ctx *ctx, int op, int dst_field, void *dst, int lhs_field, const void *lhs,
+                 int rhs_field, const void *rhs, size_t n, size_t shift, uint64_t exponent);
+/* dst[i] = lhs[i] OP constant (the *Const stages); MS_OP_FILL ignores lhs */
+int ms_pointwise_const(ms_ctx *ctx, int op, int dst_field, void *dst, int lhs_field, const void *lhs,
+                       int const_field, const uint64_t *constant, size_t n);
+/* Matrix::sum_columns (src/matrix.rs:322-394): acc[i] = sum_c col_c[i] in ONE pass */
+int ms_sum_columns(ms_ctx *ctx, int field, const void *cols, size_t col_stride_elems, unsigned ncols,
+                   size_t n, void *acc);
+
+/* ---- Merkle commitment: hash_rows + build_merkle_nodes (src/merkle.rs:412-508,
+ *      Sha256HashFn src/hash.rs:58-100) ----
+ * leaf_i = SHA-256( ||_c LE64(canonical(col_c[i])) ), Fq3 = c0||c1||c2.  digests: nrows x 32 B. */
+int ms_hash_rows_sha256(ms_ctx *ctx, int field, const void *cols, size_t col_stride_elems, unsigned ncols,
+                        size_t nrows, void *digests);
+/* nodes: n x 32 B heap layout, nodes[0] = zero digest, nodes[1] = root, nodes[n/2+i] = H(leaf 2i || leaf 2i+1) */
+int ms_merkle_nodes_sha256(ms_ctx *ctx, const void *leaves, size_t n, void *nodes);
+/* MatrixMerkleTree::from_matrix in one call; nodes may be NULL (root only); root: 32 B (host or device) */
+int ms_merkle_commit_sha256(ms_ctx *ctx, int field, const void *cols, size_t col_stride_elems, unsigned ncols,
+                            size_t nrows, void *leaves, void *nodes, void *root);
+
+/* ---- FRI: apply_drp (src/fri.rs:526-567) evaluated per coset, bit-reversed order in and out ----
+ * evals: 2^log_n elements; out: 2^(log_n-log_ff).  alpha: one element of `field`.
+ * Equals bit_reverse ∘ NTT ∘ fold ∘ (·ff) ∘ iNTT ∘ bit_reverse of the reference, in one pass. */
+int ms_fri_fold(ms_ctx *ctx, int field, const void *evals, unsigned log_n, unsigned log_ff,
+                uint64_t offset_mont, const uint64_t *alpha, void *out);
+
+/* ---- synthetic data: splitmix64, reject >= p, store x*2^64 mod p ---- */
+int ms_fill_random(ms_ctx *ctx, void *dst, size_t nwords, uint64_t seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINISTARK_B200_H */

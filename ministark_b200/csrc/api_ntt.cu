@@ -1,0 +1,433 @@
+// api_ntt.cu — NTT plans (GpuFft / GpuIfft, gpu/src/plan.rs:236-325,378-462) and the resident
+// batched forms used by Matrix::{into_polynomials,into_evaluations,into_bit_reversed_evaluations}
+// (src/matrix.rs:101-251).
+//
+// A plan is the pass list of msntt (ntt.cu) plus small device tables:
+//   tw_lo/tw_hi : omega_N^e two-level table (<= 4096 + N/4096 words) — the reference builds and
+//                 bit-reverses an n/2-word twiddle vector and an n-word scale vector on the CPU
+//                 for every plan (plan.rs:395-398, stage.rs:255-259); plans here are cached.
+//   sc_lo/sc_hi : powers of the coset offset (forward) or of offset^-1 times n^-1 (inverse).
+#include <algorithm>
+#include <cstring>
+
+#include "ctx.cuh"
+
+namespace ms {
+
+using msntt::PassParams;
+
+struct NttPlanDev {
+    NttJob job;
+    u64 N = 0;
+    unsigned estride = 1, lanes = 1, ncos = 1;
+    bool naive = false;
+    u64 root = 0;
+    std::vector<PassParams> passes;
+    std::vector<unsigned> ntiles;
+    u64 *dev = nullptr;  // one allocation holding all tables
+    msntt::Tables tb{};
+    ~NttPlanDev() {
+        if (dev) cudaFree(dev);
+    }
+};
+
+static u64 root_of_unity(unsigned log_n) {
+    u64 r = gl::to_mont(1753635133440165772ULL);
+    for (unsigned i = log_n; i < 32; i++) r = gl::sqr(r);
+    return r;
+}
+static unsigned brev_bits(unsigned v, unsigned bits) {
+    unsigned r = 0;
+    for (unsigned b = 0; b < bits; b++) r |= ((v >> b) & 1u) << (bits - 1 - b);
+    return r;
+}
+static int ilog2(u64 v) {
+    int l = 0;
+    while ((1ull << l) < v) l++;
+    return l;
+}
+
+int ntt_get_plan(ms_ctx *c, const NttJob &job, std::shared_ptr<NttPlanDev> *out) {
+    auto key = std::make_tuple(job.field, job.log_n, (int)job.inverse, job.offset, job.log_blowup, (int)job.bitrev_out);
+    auto it = c->plans.find(key);
+    if (it != c->plans.end()) {
+        *out = it->second;
+        return MS_OK;
+    }
+    auto P = std::make_shared<NttPlanDev>();
+    P->job = job;
+    const unsigned log_n = job.log_n;
+    const u64 N = 1ull << log_n;
+    P->N = N;
+    P->estride = P->lanes = (unsigned)job.field;
+    P->ncos = job.bitrev_out ? (1u << job.log_blowup) : 1u;
+    u64 root = root_of_unity(log_n);
+    if (job.inverse) root = gl::inv(root);
+    P->root = root;
+    if (log_n < 4) {
+        P->naive = true;
+        c->plans[key] = P;
+        *out = P;
+        return MS_OK;
+    }
+
+    // ---- digits and strides
+    std::vector<int> d = msntt::choose_digits(log_n);
+    const int m = (int)d.size();
+    std::vector<u64> S(m), Pw(m);
+    {
+        u64 s = 1;
+        for (int l = m - 1; l >= 0; l--) { S[l] = s; s <<= d[l]; }
+        u64 p = 1;
+        for (int l = 0; l < m; l++) { Pw[l] = p; p <<= d[l]; }
+    }
+    const bool has_pre = !job.inverse && (job.offset != gl::ONE || P->ncos > 1);
+    const bool has_post = job.inverse;
+    const u32 hi_len = (u32)std::max<u64>(1, N >> 12);
+
+    for (int k = 0; k < m; k++) {
+        PassParams p;
+        memset(&p, 0, sizeof p);
+        const u64 R = 1ull << d[k];
+        p.log_r = d[k];
+        p.n_mask = N - 1;
+        p.hi_len = hi_len;
+        p.bitrev_digit = job.bitrev_out ? 1 : 0;
+        p.lanes = P->lanes;
+        p.ncos = P->ncos;
+        p.estride = P->estride;
+        u64 W;
+        if (m == 1) {
+            W = 1;
+            p.in_rs = p.out_rs = 1;
+            p.in_r_fast = p.out_r_fast = 1;
+            p.ndims = 0;
+        } else if (k < m - 1) {  // strided pass, position preserving
+            W = std::min<u64>(1ull << (msntt::kTileLog - d[k]), S[k]);
+            p.in_rs = p.out_rs = S[k];
+            p.in_cs = p.out_cs = 1;
+            p.low_cs = 1;
+            p.ndims = 2;
+            p.dims[0] = msntt::Dim{(u32)(S[k] / W), 0, W, W, W};
+            p.dims[1] = msntt::Dim{(u32)(N / (R * S[k])), 0, R * S[k], R * S[k], 0};
+            p.has_outer = 1;
+            p.outer_mult = N / (R * S[k]);
+        } else if (!job.bitrev_out) {  // last pass, natural order: transposing write
+            W = std::min<u64>(1ull << (msntt::kTileLog - d[k]), 1ull << d[0]);
+            p.in_rs = 1;
+            p.in_cs = S[0];
+            p.out_rs = Pw[k];
+            p.out_cs = 1;
+            p.in_r_fast = 1;
+            p.out_r_fast = 0;
+            p.ndims = 1;
+            p.dims[0] = msntt::Dim{(u32)((1ull << d[0]) / W), 0, W * S[0], W, 0};
+            for (int l = 1; l < m - 1; l++) p.dims[p.ndims++] = msntt::Dim{(u32)(1ull << d[l]), 0, S[l], Pw[l], 0};
+        } else {  // last pass, bit-reversed order: contiguous, in place
+            const u64 Rprev = 1ull << d[k - 1];
+            W = std::min<u64>(1ull << (msntt::kTileLog - d[k]), Rprev);
+            p.in_rs = p.out_rs = 1;
+            p.in_cs = p.out_cs = R;
+            p.in_r_fast = p.out_r_fast = 1;
+            p.ndims = 2;
+            p.dims[0] = msntt::Dim{(u32)(Rprev / W), 0, W * R, W * R, 0};
+            p.dims[1] = msntt::Dim{(u32)(N / (R * Rprev)), 0, R * Rprev, R * Rprev, 0};
+        }
+        p.log_w = (u32)ilog2(W);
+        p.has_pre = (k == 0 && has_pre) ? 1 : 0;
+        p.has_post = (k == m - 1 && has_post) ? 1 : 0;
+        P->passes.push_back(p);
+        P->ntiles.push_back((unsigned)(N / (R * W)));
+    }
+
+    // ---- tables
+    const size_t lo_len = 4096;
+    const size_t n_tw = lo_len + hi_len;
+    const size_t n_sc = (has_pre || has_post) ? (size_t)P->ncos * (lo_len + hi_len + 1) : 0;
+    std::vector<u64> h(n_tw + n_sc);
+    {
+        u64 a = gl::ONE;
+        for (size_t e = 0; e < lo_len; e++) { h[e] = a; a = gl::mul(a, root); }
+        // a == root^4096 now
+        u64 b = gl::ONE;
+        for (size_t e = 0; e < hi_len; e++) { h[lo_len + e] = b; b = gl::mul(b, a); }
+    }
+    u64 post_step = gl::ONE;
+    if (n_sc) {
+        int st[3], nst;
+        u64 *sc_lo = h.data() + n_tw;
+        u64 *sc_hi = sc_lo + (size_t)P->ncos * lo_len;
+        u64 *pre_step = sc_hi + (size_t)P->ncos * hi_len;
+        const u64 gN = job.bitrev_out ? root_of_unity(log_n + job.log_blowup) : gl::ONE;
+        for (unsigned q = 0; q < P->ncos; q++) {
+            u64 base, cst;
+            if (has_post) {
+                base = gl::inv(job.offset);
+                cst = gl::inv(gl::to_mont(N));
+            } else {
+                // block q of a bit-reversed LDE holds the coset offset * g_N^r, r = bitrev(q)
+                const unsigned r = brev_bits(q, job.log_blowup);
+                base = gl::mul(job.offset, gl::pow(gN, r));
+                cst = gl::ONE;
+            }
+            u64 a = gl::ONE;
+            for (size_t e = 0; e < lo_len; e++) { sc_lo[q * lo_len + e] = a; a = gl::mul(a, base); }
+            u64 b = cst;
+            for (size_t e = 0; e < hi_len; e++) { sc_hi[(size_t)q * hi_len + e] = b; b = gl::mul(b, a); }
+            if (hi_len == 1) {  // single-level lookup: fold the constant into the low table
+                for (size_t e = 0; e < lo_len; e++) sc_lo[q * lo_len + e] = gl::mul(sc_lo[q * lo_len + e], cst);
+            }
+            // first step of the first pass walks the transform index in units of 2^(log_r - A)
+            msntt::steps_of(P->passes[0].log_r, st, &nst);
+            pre_step[q] = gl::pow(base, P->passes[0].in_rs << (P->passes[0].log_r - st[0]));
+            if (has_post) {
+                const PassParams &lp = P->passes.back();
+                msntt::steps_of(lp.log_r, st, &nst);
+                post_step = gl::pow(base, lp.out_rs << (lp.log_r - st[nst - 1]));
+            }
+        }
+    }
+    P->passes.back().post_step = post_step;
+    cudaError_t e = cudaMalloc(&P->dev, h.size() * 8);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(c, MS_ERR_NOMEM, "plan tables cudaMalloc: %s", cudaGetErrorString(e));
+    }
+    MS_CUDA(c, cudaMemcpyAsync(P->dev, h.data(), h.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    P->tb.t4096 = c->t4096[job.inverse ? 1 : 0];
+    P->tb.tw_lo = P->dev;
+    P->tb.tw_hi = P->dev + lo_len;
+    if (n_sc) {
+        P->tb.sc_lo = P->dev + n_tw;
+        P->tb.sc_hi = P->tb.sc_lo + (size_t)P->ncos * lo_len;
+        P->tb.pre_step = P->tb.sc_hi + (size_t)P->ncos * hi_len;
+    }
+    c->plans[key] = P;
+    *out = P;
+    return MS_OK;
+}
+
+__global__ void copy_strided_kernel(const u64 *src, size_t src_stride, u64 *dst, size_t dst_stride, size_t words) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < words) dst[blockIdx.y * dst_stride + i] = src[blockIdx.y * src_stride + i];
+}
+
+int ntt_run(ms_ctx *c, NttPlanDev &P, const u64 *in, size_t in_cs, u64 *out, size_t out_cs, unsigned ncols) {
+    if (ncols == 0) return MS_OK;
+    const u64 N = P.N;
+    const size_t col_words = (size_t)N * P.estride;
+    const bool lde = P.job.bitrev_out;
+    const size_t tmp_budget = (size_t)1 << 30;
+    unsigned max_cols = 65535u / (P.lanes * P.ncos);
+    const int m = (int)P.passes.size();
+    const bool need_tmp = P.naive ? (in == out) : (!lde && m >= 2);
+    if (need_tmp) max_cols = (unsigned)std::max<size_t>(1, std::min<size_t>(max_cols, tmp_budget / (col_words * 8)));
+    for (unsigned c0 = 0; c0 < ncols; c0 += max_cols) {
+        const unsigned nc = std::min(max_cols, ncols - c0);
+        const u64 *src = in + (size_t)c0 * in_cs;
+        u64 *dst = out + (size_t)c0 * out_cs;
+        u64 *tmp = nullptr;
+        if (need_tmp) {
+            void *t;
+            int rc = scratch_get(c, 0, (size_t)nc * col_words * 8, &t);
+            if (rc) return rc;
+            tmp = (u64 *)t;
+        }
+        if (P.naive) {
+            if (lde) return fail(c, MS_ERR_INVALID, "internal: naive plan in LDE mode");
+            u64 *o = need_tmp ? tmp : dst;
+            const size_t ocs = need_tmp ? col_words : out_cs;
+            msntt::launch_naive(src, in_cs, o, ocs, P.job.log_n, P.estride, P.lanes, nc, P.job.inverse, P.root,
+                                P.job.offset, c->stream);
+            c->launches++;
+            MS_CHECK_LAUNCH(c);
+            if (need_tmp) {
+                dim3 g((unsigned)((col_words + 255) / 256), nc);
+                copy_strided_kernel<<<g, 256, 0, c->stream>>>(tmp, col_words, dst, out_cs, col_words);
+                c->launches++;
+                MS_CHECK_LAUNCH(c);
+            }
+            continue;
+        }
+        for (int k = 0; k < m; k++) {
+            PassParams p = P.passes[k];
+            const u64 *pin;
+            u64 *pout;
+            if (lde) {
+                pin = (k == 0) ? src : dst;
+                pout = dst;
+                p.in_col_stride = (k == 0) ? in_cs : out_cs;
+                p.out_col_stride = out_cs;
+                p.in_cos_stride = (k == 0) ? 0 : col_words;
+                p.out_cos_stride = col_words;
+            } else if (m == 1) {
+                pin = src;
+                pout = dst;
+                p.in_col_stride = in_cs;
+                p.out_col_stride = out_cs;
+            } else {
+                pin = (k == 0) ? src : tmp;
+                pout = (k == m - 1) ? dst : tmp;
+                p.in_col_stride = (k == 0) ? in_cs : col_words;
+                p.out_col_stride = (k == m - 1) ? out_cs : col_words;
+            }
+            msntt::launch_pass(p, P.tb, P.job.inverse, pin, pout, P.ntiles[k], nc * P.lanes * P.ncos, c->stream);
+            c->launches++;
+            MS_CHECK_LAUNCH(c);
+        }
+    }
+    return MS_OK;
+}
+
+static int check_field(ms_ctx *c, int field) {
+    if (field != MS_FIELD_FP && field != MS_FIELD_FQ3) return fail(c, MS_ERR_INVALID, "unknown field id %d", field);
+    return MS_OK;
+}
+
+}  // namespace ms
+
+using namespace ms;
+
+struct ms_ntt_plan {
+    ms_ctx *ctx;
+    std::shared_ptr<NttPlanDev> plan;
+    std::vector<void *> queue;
+};
+
+extern "C" {
+
+int ms_ntt_plan_create(ms_ctx *c, int field, unsigned log_n, int direction, uint64_t offset_mont, ms_ntt_plan **out) {
+    if (!c || !out) return MS_ERR_INVALID;
+    if (int rc = check_field(c, field)) return rc;
+    if (log_n > 32) return fail(c, MS_ERR_INVALID, "log_n %u out of range [0, 32]", log_n);
+    if (direction != MS_NTT_FORWARD && direction != MS_NTT_INVERSE) return fail(c, MS_ERR_INVALID, "bad direction");
+    if (offset_mont >= gl::P || offset_mont == 0) return fail(c, MS_ERR_INVALID, "offset must be a non-zero canonical word");
+    NttJob job{field, log_n, direction == MS_NTT_INVERSE, false, 0, offset_mont};
+    auto *pl = new ms_ntt_plan();
+    pl->ctx = c;
+    int rc = ntt_get_plan(c, job, &pl->plan);
+    if (rc) {
+        delete pl;
+        return rc;
+    }
+    *out = pl;
+    return MS_OK;
+}
+
+int ms_ntt_encode(ms_ntt_plan *pl, void *column) {
+    if (!pl || !column) return MS_ERR_INVALID;
+    pl->queue.push_back(column);
+    return MS_OK;
+}
+
+int ms_ntt_execute(ms_ntt_plan *pl) {
+    if (!pl) return MS_ERR_INVALID;
+    ms_ctx *c = pl->ctx;
+    NttPlanDev &P = *pl->plan;
+    const size_t col_words = (size_t)P.N * P.estride;
+    std::vector<void *> host_cols, dev_cols;
+    for (void *p : pl->queue) (is_device_ptr(p) ? dev_cols : host_cols).push_back(p);
+    pl->queue.clear();
+    int rc = MS_OK;
+    for (void *p : dev_cols) {
+        rc = ntt_run(c, P, (const u64 *)p, col_words, (u64 *)p, col_words, 1);
+        if (rc) return rc;
+    }
+    if (!host_cols.empty()) {
+        // stage all host columns into one device matrix, one batched transform, copy back
+        const size_t tmp_budget = (size_t)4 << 30;
+        const size_t per = std::max<size_t>(1, tmp_budget / (col_words * 8));
+        for (size_t i0 = 0; i0 < host_cols.size(); i0 += per) {
+            const size_t nc = std::min(per, host_cols.size() - i0);
+            void *stage;
+            rc = scratch_get(c, 1, nc * col_words * 8, &stage);
+            if (rc) return rc;
+            for (size_t i = 0; i < nc; i++)
+                MS_CUDA(c, cudaMemcpyAsync((u64 *)stage + i * col_words, host_cols[i0 + i], col_words * 8,
+                                           cudaMemcpyHostToDevice, c->stream));
+            rc = ntt_run(c, P, (const u64 *)stage, col_words, (u64 *)stage, col_words, (unsigned)nc);
+            if (rc) return rc;
+            for (size_t i = 0; i < nc; i++)
+                MS_CUDA(c, cudaMemcpyAsync(host_cols[i0 + i], (u64 *)stage + i * col_words, col_words * 8,
+                                           cudaMemcpyDeviceToHost, c->stream));
+            MS_CUDA(c, cudaStreamSynchronize(c->stream));
+        }
+    }
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MS_OK;
+}
+
+int ms_ntt_plan_destroy(ms_ntt_plan *pl) {
+    if (!pl) return MS_ERR_INVALID;
+    delete pl;
+    return MS_OK;
+}
+
+int ms_ntt_batch(ms_ctx *c, int field, void *data, size_t col_stride_elems, unsigned ncols, unsigned log_n,
+                 int direction, uint64_t offset_mont) {
+    if (!c || !data) return MS_ERR_INVALID;
+    if (int rc = check_field(c, field)) return rc;
+    if (log_n > 32 || ncols == 0) return fail(c, MS_ERR_INVALID, "ms_ntt_batch: bad size");
+    if (offset_mont >= gl::P || offset_mont == 0) return fail(c, MS_ERR_INVALID, "offset must be a non-zero canonical word");
+    const size_t n = (size_t)1 << log_n;
+    if (ncols > 1 && col_stride_elems < n) return fail(c, MS_ERR_INVALID, "ms_ntt_batch: stride < n");
+    NttJob job{field, log_n, direction == MS_NTT_INVERSE, false, 0, offset_mont};
+    std::shared_ptr<NttPlanDev> P;
+    if (int rc = ntt_get_plan(c, job, &P)) return rc;
+    const size_t span = ((size_t)(ncols - 1) * col_stride_elems + n) * field * 8;
+    Staged d(c, data, span, true, true);
+    if (d.rc) return d.rc;
+    int rc = ntt_run(c, *P, d.as<u64>(), col_stride_elems * field, d.as<u64>(), col_stride_elems * field, ncols);
+    if (rc) return rc;
+    return d.finish();
+}
+
+__global__ void pad_copy_kernel(const u64 *src, size_t src_stride, u64 *dst, size_t dst_stride, size_t n_words,
+                                size_t N_words) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < N_words) dst[blockIdx.y * dst_stride + i] = i < n_words ? src[blockIdx.y * src_stride + i] : 0;
+}
+
+int ms_lde_batch(ms_ctx *c, int field, const void *coeffs, size_t in_stride_elems, void *evals, size_t out_stride_elems,
+                 unsigned ncols, unsigned log_n, unsigned log_blowup, uint64_t offset_mont, int bitrev_out) {
+    if (!c || !coeffs || !evals) return MS_ERR_INVALID;
+    if (int rc = check_field(c, field)) return rc;
+    if (log_n + log_blowup > 32 || log_blowup > 6 || ncols == 0) return fail(c, MS_ERR_INVALID, "ms_lde_batch: bad size");
+    if (offset_mont >= gl::P || offset_mont == 0) return fail(c, MS_ERR_INVALID, "offset must be a non-zero canonical word");
+    const size_t n = (size_t)1 << log_n, N = n << log_blowup;
+    if (ncols > 1 && (in_stride_elems < n || out_stride_elems < N)) return fail(c, MS_ERR_INVALID, "ms_lde_batch: stride too small");
+    Staged in(c, coeffs, ((size_t)(ncols - 1) * in_stride_elems + n) * field * 8, true, false);
+    if (in.rc) return in.rc;
+    Staged out(c, evals, ((size_t)(ncols - 1) * out_stride_elems + N) * field * 8, false, true);
+    if (out.rc) return out.rc;
+    int rc;
+    if (bitrev_out && log_n >= 4) {
+        NttJob job{field, log_n, false, true, log_blowup, offset_mont};
+        std::shared_ptr<NttPlanDev> P;
+        if ((rc = ntt_get_plan(c, job, &P))) return rc;
+        rc = ntt_run(c, *P, in.as<u64>(), in_stride_elems * field, out.as<u64>(), out_stride_elems * field, ncols);
+        if (rc) return rc;
+    } else {
+        // natural order (Matrix::into_evaluations, src/matrix.rs:192-208: resize with zeros, then
+        // a full-size coset NTT), or a tiny transform: zero-pad on device and run the size-N plan.
+        dim3 g((unsigned)((N * field + 255) / 256), ncols);
+        pad_copy_kernel<<<g, 256, 0, c->stream>>>(in.as<u64>(), in_stride_elems * field, out.as<u64>(),
+                                                  out_stride_elems * field, n * field, N * field);
+        c->launches++;
+        MS_CHECK_LAUNCH(c);
+        NttJob job{field, log_n + log_blowup, false, false, 0, offset_mont};
+        std::shared_ptr<NttPlanDev> P;
+        if ((rc = ntt_get_plan(c, job, &P))) return rc;
+        rc = ntt_run(c, *P, out.as<u64>(), out_stride_elems * field, out.as<u64>(), out_stride_elems * field, ncols);
+        if (rc) return rc;
+        if (bitrev_out) {
+            rc = ms_bit_reverse(c, field, out.dev, out_stride_elems, ncols, log_n + log_blowup);
+            if (rc) return rc;
+        }
+    }
+    if ((rc = in.finish())) return rc;
+    return out.finish();
+}
+
+}  // extern "C"

@@ -1,0 +1,164 @@
+// field.cuh — Goldilocks Fp (p = 2^64 - 2^32 + 1) and Fq3 = Fp[X]/(X^3 - 2) device arithmetic.
+//
+// Memory representation is the reference's: every 64-bit word is the canonical (< p)
+// Montgomery residue x * 2^64 mod p (gpu/src/metal/felt_u64.h.metal:118,127; the Rust
+// side builds constants as raw Montgomery BigInts, gpu/src/fields.rs:82).  These
+// routines are the sm_100a counterpart of felt_u64.h.metal:147-177 (Fp) and :205-236
+// (Fq3), re-derived rather than transcribed:
+//
+//   * mont_mul: 64x64->128 product (4 IMAD.WIDE) followed by the Goldilocks-special
+//     Montgomery reduction  t = hi - (a - (a >> 32) - e),  a = lo + (lo << 32) (carry e),
+//     which needs no second multiplication because -p^{-1} = -(2^32 + 1) mod 2^64.
+//     The result is canonical whenever one operand is canonical; the other operand may
+//     be ANY u64 ("lazy" value), which the NTT butterflies exploit.
+//   * lazy add/sub: values in [0, 2^64) representing themselves mod p.  2^64 = eps
+//     (mod p) with eps = 2^32 - 1, so a carry out of 64 bits is repaired by adding eps
+//     and a borrow by subtracting eps.
+//
+// Integer modular arithmetic only: tensor cores are not applicable.
+#pragma once
+#include <cstdint>
+
+namespace gl {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+constexpr u64 P = 0xFFFFFFFF00000001ULL;
+constexpr u64 EPS = 0xFFFFFFFFULL;        // 2^64 mod p  == Montgomery form of 1
+constexpr u64 ONE = EPS;
+constexpr u64 R2 = 0xFFFFFFFE00000001ULL; // 2^128 mod p
+constexpr u64 TWO = 0x1FFFFFFFEULL;       // Montgomery form of 2 (Fq3 non-residue)
+
+#if defined(__CUDACC__)
+#define GL_DEV __device__ __forceinline__
+#define GL_HD __host__ __device__ __forceinline__
+#else
+#define GL_DEV inline
+#define GL_HD inline
+#endif
+
+// ---- canonical <-> canonical ------------------------------------------------------
+GL_HD u64 canon(u64 x) { return x >= P ? x - P : x; }
+
+GL_HD u64 add(u64 a, u64 b) {  // a, b < p
+    u64 s = a + b;
+    u64 t = s + EPS;           // s - p (mod 2^64)
+    return (s < a || t < s) ? t : s;
+}
+GL_HD u64 sub(u64 a, u64 b) {  // a, b < p
+    u64 d = a - b;
+    return a < b ? d - EPS : d;  // + p
+}
+GL_HD u64 neg(u64 a) { return a ? P - a : 0; }
+
+// ---- lazy arithmetic (any u64 in, any u64 out; value preserved mod p) ---------------
+// lc: second operand canonical (< p)  -> a single repair suffices.
+GL_HD u64 add_lc(u64 a, u64 t) {
+    u64 s = a + t;
+    return s < a ? s + EPS : s;
+}
+GL_HD u64 sub_lc(u64 a, u64 t) {
+    u64 d = a - t;
+    return a < t ? d - EPS : d;
+}
+// ll: both operands arbitrary u64 -> up to two repairs.
+GL_HD u64 add_ll(u64 a, u64 b) {
+    u64 s = a + b;
+    if (s < a) { u64 s2 = s + EPS; s = s2 < s ? s2 + EPS : s2; }
+    return s;
+}
+GL_HD u64 sub_ll(u64 a, u64 b) {
+    u64 d = a - b;
+    if (a < b) { u64 d2 = d - EPS; d = d < EPS ? d2 - EPS : d2; }
+    return d;
+}
+
+// ---- Montgomery multiplication ---------------------------------------------------------
+// returns a*b*2^-64 mod p, canonical, provided a*b < p * 2^64 (i.e. one operand < p).
+GL_HD u64 mont_reduce(u64 hi, u64 lo) {
+    u64 a = lo + (lo << 32);
+    u64 e = a < lo;                    // carry out of the 64-bit add
+    u64 b = a - (a >> 32) - e;         // never underflows: a >= (a>>32) + e
+    u64 r = hi - b;
+    return hi < b ? r - EPS : r;       // + p
+}
+GL_HD u64 mul(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+    return mont_reduce(__umul64hi(a, b), a * b);
+#else
+    unsigned __int128 x = (unsigned __int128)a * b;
+    return mont_reduce((u64)(x >> 64), (u64)x);
+#endif
+}
+GL_HD u64 sqr(u64 a) { return mul(a, a); }
+GL_HD u64 to_mont(u64 x_canon) { return mul(x_canon, R2); }
+GL_HD u64 from_mont(u64 w) { return mul(w, 1); }
+
+GL_HD u64 pow(u64 a, u64 e) {
+    u64 r = ONE;
+    while (e) {
+        if (e & 1) r = mul(r, a);
+        a = sqr(a);
+        e >>= 1;
+    }
+    return r;
+}
+// a^(p-2) = a^(2^64 - 2^32 - 1); exponent bits MSB first: 31 ones, one zero, 32 ones.
+// Built from a^(2^k - 1) blocks, ~73 multiplications (the reference uses a chain of
+// similar length, felt_u64.h.metal:97-109).
+GL_HD u64 inv(u64 a) {
+    u64 x1 = a;
+    u64 x2 = mul(sqr(x1), x1);                 // 2^2-1
+    u64 x3 = mul(sqr(x2), x1);                 // 2^3-1
+    u64 x6 = x3; for (int i = 0; i < 3; i++) x6 = sqr(x6); x6 = mul(x6, x3);
+    u64 x12 = x6; for (int i = 0; i < 6; i++) x12 = sqr(x12); x12 = mul(x12, x6);
+    u64 x24 = x12; for (int i = 0; i < 12; i++) x24 = sqr(x24); x24 = mul(x24, x12);
+    u64 x30 = x24; for (int i = 0; i < 6; i++) x30 = sqr(x30); x30 = mul(x30, x6);
+    u64 x31 = mul(sqr(x30), x1);
+    u64 x32 = mul(sqr(x31), x1);
+    u64 r = x31;                                // top 31 ones
+    for (int i = 0; i < 33; i++) r = sqr(r);    // the zero bit + 32 more positions
+    return mul(r, x32);                         // low 32 ones
+}
+
+// ---- Fq3 ---------------------------------------------------------------------------------
+struct Fq3 {
+    u64 c0, c1, c2;
+};
+GL_HD Fq3 fq3(u64 a) { return Fq3{a, 0, 0}; }
+GL_HD Fq3 add(Fq3 a, Fq3 b) { return Fq3{add(a.c0, b.c0), add(a.c1, b.c1), add(a.c2, b.c2)}; }
+GL_HD Fq3 sub(Fq3 a, Fq3 b) { return Fq3{sub(a.c0, b.c0), sub(a.c1, b.c1), sub(a.c2, b.c2)}; }
+GL_HD Fq3 neg(Fq3 a) { return Fq3{neg(a.c0), neg(a.c1), neg(a.c2)}; }
+GL_HD Fq3 mul(Fq3 a, u64 b) { return Fq3{mul(a.c0, b), mul(a.c1, b), mul(a.c2, b)}; }
+// (a0 + a1 X + a2 X^2)(b0 + b1 X + b2 X^2) mod X^3 - 2, 6 base multiplications
+// (Karatsuba-style cross terms; same field element as felt_u64.h.metal:205-231).
+GL_HD Fq3 mul(Fq3 a, Fq3 b) {
+    u64 v0 = mul(a.c0, b.c0), v1 = mul(a.c1, b.c1), v2 = mul(a.c2, b.c2);
+    u64 x12 = sub(sub(mul(add(a.c1, a.c2), add(b.c1, b.c2)), v1), v2);  // a1b2 + a2b1
+    u64 x01 = sub(sub(mul(add(a.c0, a.c1), add(b.c0, b.c1)), v0), v1);  // a0b1 + a1b0
+    u64 x02 = sub(sub(mul(add(a.c0, a.c2), add(b.c0, b.c2)), v0), v2);  // a0b2 + a2b0
+    return Fq3{add(v0, add(x12, x12)), add(x01, add(v2, v2)), add(x02, v1)};
+}
+GL_HD Fq3 sqr(Fq3 a) { return mul(a, a); }
+GL_HD Fq3 pow(Fq3 a, u64 e) {
+    Fq3 r = fq3(ONE);
+    while (e) {
+        if (e & 1) r = mul(r, a);
+        a = sqr(a);
+        e >>= 1;
+    }
+    return r;
+}
+// inverse through the norm to Fp (the reference leaves Fq3::inverse unimplemented,
+// felt_u64.h.metal:267-270; eval_cpu.rs uses ark-ff's CubicExtField::inverse).
+GL_HD Fq3 inv(Fq3 a) {
+    u64 s0 = sub(sqr(a.c0), mul(TWO, mul(a.c1, a.c2)));
+    u64 s1 = sub(mul(TWO, sqr(a.c2)), mul(a.c0, a.c1));
+    u64 s2 = sub(sqr(a.c1), mul(a.c0, a.c2));
+    u64 nrm = add(mul(a.c0, s0), mul(TWO, add(mul(a.c2, s1), mul(a.c1, s2))));
+    u64 ni = inv(nrm);
+    return Fq3{mul(s0, ni), mul(s1, ni), mul(s2, ni)};
+}
+
+}  // namespace gl

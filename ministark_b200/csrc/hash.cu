@@ -1,0 +1,221 @@
+// hash.cu — SHA-256 Merkle commitment of a column-major field matrix.
+//
+// Replaces the reference's CPU path (it never hashes on the GPU):
+//   hash_rows            src/merkle.rs:412-436   leaf_i = SHA-256(row i serialized)
+//   hash_elements        src/hash.rs:92-99       ark-serialize: canonical value, 8 bytes LE each,
+//                                                Fq3 = c0 || c1 || c2
+//   build_merkle_nodes   src/merkle.rs:438-508   heap layout, nodes[k] = H(nodes[2k] || nodes[2k+1])
+//   merge                src/hash.rs:77-82       SHA-256 over the 64 digest bytes
+//
+// One thread per row: the column-major LDE is read directly (coalesced across threads since
+// consecutive threads take consecutive rows), each word is taken out of Montgomery form with
+// one reduction, byte-swapped into the big-endian SHA message schedule and compressed.  This
+// kernel is INT32-ALU bound (about 2k instructions per 64-byte block), not HBM bound.
+#include "ctx.cuh"
+
+namespace ms {
+
+__constant__ u32 c_K[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+    0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+    0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+    0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+    0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+    0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+    0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+
+__device__ __forceinline__ u32 rotr(u32 x, int r) { return __funnelshift_r(x, x, r); }
+__device__ __forceinline__ u32 bswap(u32 x) { return __byte_perm(x, 0, 0x0123); }
+
+struct Sha {
+    u32 h[8];
+    __device__ __forceinline__ void init() {
+        h[0] = 0x6a09e667; h[1] = 0xbb67ae85; h[2] = 0x3c6ef372; h[3] = 0xa54ff53a;
+        h[4] = 0x510e527f; h[5] = 0x9b05688c; h[6] = 0x1f83d9ab; h[7] = 0x5be0cd19;
+    }
+    // w: 16 message words (big-endian interpreted), destroyed
+    __device__ __forceinline__ void compress(u32 (&w)[16]) {
+        u32 a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            if (i >= 16) {
+                u32 w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+                u32 s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3);
+                u32 s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10);
+                w[i & 15] = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
+            }
+            u32 S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
+            u32 ch = (e & f) ^ (~e & g);
+            u32 t1 = hh + S1 + ch + c_K[i] + w[i & 15];
+            u32 S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
+            u32 mj = (a & b) ^ (a & c) ^ (b & c);
+            u32 t2 = S0 + mj;
+            hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        }
+        h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+    }
+    // digest bytes = big-endian state words
+    __device__ __forceinline__ void store(u32 *out) const {
+        uint4 lo = make_uint4(bswap(h[0]), bswap(h[1]), bswap(h[2]), bswap(h[3]));
+        uint4 hi = make_uint4(bswap(h[4]), bswap(h[5]), bswap(h[6]), bswap(h[7]));
+        reinterpret_cast<uint4 *>(out)[0] = lo;
+        reinterpret_cast<uint4 *>(out)[1] = hi;
+    }
+};
+
+// words_per_row = ncols * lanes 64-bit words; word t of row i lives at
+// cols[(t / lanes) * col_stride_words + i * lanes + t % lanes].
+__global__ void __launch_bounds__(128) hash_rows_kernel(const u64 *__restrict__ cols, size_t col_stride_words,
+                                                         unsigned lanes, unsigned words_per_row, size_t nrows,
+                                                         u32 *__restrict__ digests) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    Sha s;
+    s.init();
+    const unsigned msg_words32 = words_per_row * 2;
+    const unsigned total32 = ((msg_words32 + 1 + 2 + 15) / 16) * 16;  // 0x80 marker + 64-bit length
+    const u64 bitlen = (u64)words_per_row * 64;
+    const u64 *row = cols + i * lanes;
+    unsigned t = 0, cidx = 0, l = 0;  // running word index -> (column, lane)
+    for (unsigned blk = 0; blk * 16 < total32; blk++) {
+        u32 w[16];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const unsigned g = blk * 16 + 2 * j;
+            u32 lo = 0, hi = 0;
+            if (t < words_per_row) {
+                u64 x = gl::from_mont(row[(size_t)cidx * col_stride_words + l]);
+                lo = bswap((u32)x);
+                hi = bswap((u32)(x >> 32));
+                t++;
+                if (++l == lanes) { l = 0; cidx++; }
+            } else {
+                if (g == msg_words32) lo = 0x80000000u;
+                if (g == total32 - 2) { lo = (u32)(bitlen >> 32); hi = (u32)bitlen; }
+            }
+            w[2 * j] = lo;
+            w[2 * j + 1] = hi;
+        }
+        s.compress(w);
+    }
+    s.store(digests + i * 8);
+}
+
+// dst[k] = SHA-256(src[2k] || src[2k+1]) for k in [0, count): one Merkle level.
+__global__ void __launch_bounds__(128) merkle_level_kernel(const u32 *__restrict__ src, u32 *__restrict__ dst,
+                                                            size_t count) {
+    const size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    Sha s;
+    s.init();
+    u32 w[16];
+    const uint4 *p = reinterpret_cast<const uint4 *>(src + k * 16);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint4 v = p[q];
+        w[4 * q] = bswap(v.x); w[4 * q + 1] = bswap(v.y); w[4 * q + 2] = bswap(v.z); w[4 * q + 3] = bswap(v.w);
+    }
+    s.compress(w);
+#pragma unroll
+    for (int j = 0; j < 16; j++) w[j] = 0;
+    w[0] = 0x80000000u;
+    w[15] = 512;
+    s.compress(w);
+    s.store(dst + k * 8);
+}
+
+static int hash_rows_dev(ms_ctx *c, int field, const u64 *cols, size_t col_stride_elems, unsigned ncols, size_t nrows,
+                         u32 *digests) {
+    if (nrows == 0) return MS_OK;
+    const unsigned threads = 128;
+    hash_rows_kernel<<<(unsigned)((nrows + threads - 1) / threads), threads, 0, c->stream>>>(
+        cols, col_stride_elems * field, (unsigned)field, ncols * field, nrows, digests);
+    c->launches++;
+    MS_CHECK_LAUNCH(c);
+    return MS_OK;
+}
+
+static int merkle_nodes_dev(ms_ctx *c, const u32 *leaves, size_t n, u32 *nodes) {
+    MS_CUDA(c, cudaMemsetAsync(nodes, 0, 32, c->stream));
+    const unsigned threads = 128;
+    // leaf pairs -> nodes[n/2 .. n)
+    merkle_level_kernel<<<(unsigned)((n / 2 + threads - 1) / threads), threads, 0, c->stream>>>(leaves, nodes + (n / 2) * 8,
+                                                                                                n / 2);
+    c->launches++;
+    MS_CHECK_LAUNCH(c);
+    for (size_t size = n / 4; size >= 1; size >>= 1) {
+        // nodes[size .. 2 size) from nodes[2 size .. 4 size)
+        merkle_level_kernel<<<(unsigned)((size + threads - 1) / threads), threads, 0, c->stream>>>(
+            nodes + 2 * size * 8, nodes + size * 8, size);
+        c->launches++;
+        MS_CHECK_LAUNCH(c);
+    }
+    return MS_OK;
+}
+
+}  // namespace ms
+
+using namespace ms;
+
+extern "C" {
+
+int ms_hash_rows_sha256(ms_ctx *c, int field, const void *cols, size_t col_stride_elems, unsigned ncols, size_t nrows,
+                        void *digests) {
+    if (!c || !cols || !digests) return MS_ERR_INVALID;
+    if (field != MS_FIELD_FP && field != MS_FIELD_FQ3) return fail(c, MS_ERR_INVALID, "unknown field id %d", field);
+    if (ncols == 0) return fail(c, MS_ERR_INVALID, "ms_hash_rows_sha256: no columns");
+    if (ncols > 1 && col_stride_elems < nrows) return fail(c, MS_ERR_INVALID, "ms_hash_rows_sha256: stride < nrows");
+    Staged in(c, cols, ((size_t)(ncols - 1) * col_stride_elems + nrows) * field * 8, true, false);
+    if (in.rc) return in.rc;
+    Staged out(c, digests, nrows * 32, false, true);
+    if (out.rc) return out.rc;
+    int rc = hash_rows_dev(c, field, in.as<u64>(), col_stride_elems, ncols, nrows, out.as<u32>());
+    if (rc) return rc;
+    if ((rc = in.finish())) return rc;
+    return out.finish();
+}
+
+int ms_merkle_nodes_sha256(ms_ctx *c, const void *leaves, size_t n, void *nodes) {
+    if (!c || !leaves || !nodes) return MS_ERR_INVALID;
+    // MerkleTreeImpl::new: at least two leaves, power of two (src/merkle.rs:113-128)
+    if (n < 2 || (n & (n - 1))) return fail(c, MS_ERR_INVALID, "merkle tree needs a power-of-two number of leaves >= 2, got %zu", n);
+    Staged in(c, leaves, n * 32, true, false);
+    if (in.rc) return in.rc;
+    Staged out(c, nodes, n * 32, false, true);
+    if (out.rc) return out.rc;
+    int rc = merkle_nodes_dev(c, in.as<u32>(), n, out.as<u32>());
+    if (rc) return rc;
+    if ((rc = in.finish())) return rc;
+    return out.finish();
+}
+
+int ms_merkle_commit_sha256(ms_ctx *c, int field, const void *cols, size_t col_stride_elems, unsigned ncols, size_t nrows,
+                            void *leaves, void *nodes, void *root) {
+    if (!c || !cols || !root) return MS_ERR_INVALID;
+    if (field != MS_FIELD_FP && field != MS_FIELD_FQ3) return fail(c, MS_ERR_INVALID, "unknown field id %d", field);
+    if (ncols == 0) return fail(c, MS_ERR_INVALID, "ms_merkle_commit_sha256: no columns");
+    if (nrows < 2 || (nrows & (nrows - 1))) return fail(c, MS_ERR_INVALID, "merkle tree needs a power-of-two number of leaves >= 2, got %zu", nrows);
+    if (ncols > 1 && col_stride_elems < nrows) return fail(c, MS_ERR_INVALID, "ms_merkle_commit_sha256: stride < nrows");
+    Staged in(c, cols, ((size_t)(ncols - 1) * col_stride_elems + nrows) * field * 8, true, false);
+    if (in.rc) return in.rc;
+    int rc;
+    void *lv = nullptr, *nd = nullptr;
+    Staged lout(c, leaves, leaves ? nrows * 32 : 0, false, true);
+    if (lout.rc) return lout.rc;
+    Staged nout(c, nodes, nodes ? nrows * 32 : 0, false, true);
+    if (nout.rc) return nout.rc;
+    if (leaves) lv = lout.dev;
+    else if ((rc = scratch_get(c, 2, nrows * 32, &lv))) return rc;
+    if (nodes) nd = nout.dev;
+    else if ((rc = scratch_get(c, 3, nrows * 32, &nd))) return rc;
+    if ((rc = hash_rows_dev(c, field, in.as<u64>(), col_stride_elems, ncols, nrows, (u32 *)lv))) return rc;
+    if ((rc = merkle_nodes_dev(c, (const u32 *)lv, nrows, (u32 *)nd))) return rc;
+    MS_CUDA(c, cudaMemcpyAsync(root, (const char *)nd + 32, 32, cudaMemcpyDefault, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if ((rc = in.finish())) return rc;
+    if ((rc = lout.finish())) return rc;
+    return nout.finish();
+}
+
+}  // extern "C"

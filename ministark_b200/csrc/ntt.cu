@@ -1,0 +1,313 @@
+// ntt.cu — multi-pass radix-2^k number-theoretic transform over Goldilocks for sm_100a.
+//
+// Replaces the reference's FftSingle / FftMultiple / BitReverse / MulAssign kernel chain
+// (gpu/src/metal/fft_shaders.h.metal:13-101, encoded by gpu/src/plan.rs:427-450), which
+// makes log2(n)-10 global passes + a threadgroup pass + a bit-reverse pass + a scale pass.
+// Here a 2^24-point column takes THREE global passes in total and nothing else:
+//
+//   N = R_1 * R_2 * ... * R_m  (digits of <= 8 bits; a single digit of <= 12 bits if N <= 4096)
+//   pass k: each CTA stages a [R_k][W] tile (<= 4096 elements) in shared memory, runs W
+//           R_k-point sub-NTTs with radix-16/8/4/2 in-register butterflies (DIT networks,
+//           lazy 64-bit arithmetic, twiddles of the in-register levels are compile-time
+//           constants), multiplies by the inter-pass twiddles omega_{N_k}^(i_k * lower) generated
+//           per thread as a geometric progression from a two-level table, and writes back.
+//   * coset scaling (offset^j on the way in) and inverse scaling (n^-1 offset^-i on the way out)
+//     are fused into the first / last pass; the reference's extra MulAssign pass
+//     (ScaleAndNormalizeGpuStage, gpu/src/stage.rs:235-277) and its CPU-built n-entry scale
+//     vector disappear.
+//   * natural-order output: the last pass writes transposed (digit-reversed) tiles, so no
+//     BitReverse pass.  bit-reversed output (what commitments use, src/matrix.rs:225-234):
+//     every pass is position-preserving and the digit is left bit-reversed, so the
+//     reference's GPU bit-reverse followed by a CPU bit-reverse vanish as well.
+//
+// Integer ALU bound (64-bit modular arithmetic on 32-bit lanes); tensor cores do not apply.
+#include "ntt.cuh"
+
+#include "dft.cuh"
+
+#include <cstdio>
+#include <type_traits>
+
+namespace msntt {
+
+using namespace gl;
+
+void upload_constants() {}
+
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 brev_rt(u32 k, int bits) { return bits ? (__brev(k) >> (32 - bits)) : 0; }
+
+__device__ __forceinline__ u32 padi(u32 i) { return i + (i >> 4); }
+
+struct TileCtx {
+    u64 in_base, out_base, low_base;
+    const u64 *sc_lo, *sc_hi;
+    u64 pre_step;
+};
+
+__device__ __forceinline__ u64 tw_lookup(const u64 *lo, const u64 *hi, u32 hi_len, u64 e) {
+    u64 t = lo[e & 4095];
+    if (hi_len > 1) t = mul(hi[e >> 12], t);
+    return t;
+}
+
+// One radix-2^B step of the CTA-level sub-NTT.  f = bit position of the field inside the linear
+// tile index (r * W + c); lbits = number of r-bits below the field; iR_* describe the fields
+// already transformed (needed by the last step only).
+template <int B, bool INV, bool FIRST, bool LAST, int B1, int B2, int LOGR>
+__device__ __forceinline__ void do_step(u64 *sm, const PassParams &p, const Tables &tb, const TileCtx &tc,
+                                        const int f, const int lbits) {
+    constexpr int RAD = 1 << B;
+    constexpr int G = kElemsPerThread >> B;
+    const u32 nthreads = blockDim.x, tid = threadIdx.x;
+    const u32 wmask = (1u << p.log_w) - 1;
+#pragma unroll 1
+    for (int gi = 0; gi < G; gi++) {
+        const u32 g = gi * nthreads + tid;
+        const u32 i0 = ((g >> f) << (f + B)) | (g & ((1u << f) - 1));
+        const u32 c = i0 & wmask, rpos0 = i0 >> p.log_w;
+        u64 x[RAD];
+        static_for<0, RAD>([&](auto K) { x[K] = sm[padi(i0 + ((u32)K << f))]; });
+
+        if (FIRST && p.has_pre) {
+            // x[k] *= q^(in index), in index = A + k * (in_rs << (f - log_w))
+            u64 A = tc.in_base + (u64)rpos0 * p.in_rs + (u64)c * p.in_cs;
+            u64 t = tw_lookup(tc.sc_lo, tc.sc_hi, p.hi_len, A);
+            static_for<0, RAD>([&](auto K) {
+                x[K] = mul(x[K], t);
+                if constexpr (decltype(K)::value + 1 < RAD) t = mul(t, tc.pre_step);
+            });
+        }
+
+        dft_regs<B, INV>(x);
+
+        if (!LAST) {
+            // inner twiddle omega_{R_m}^(kappa * rlow), R_m = 2^(lbits+B)
+            const u32 rlow = rpos0 & ((1u << lbits) - 1);
+            const int sh = 12 - lbits - B;
+            static_for<1, RAD>([&](auto KAP) {
+                constexpr int q = brev_c(decltype(KAP)::value, B);
+                x[q] = mul(x[q], __ldg(tb.t4096 + (((u32)KAP * rlow) << sh)));
+            });
+            x[0] = canon(x[0]);
+        } else {
+            // output index of this pass's digit contributed by the earlier fields
+            u32 iR0 = 0;
+            if (B1 > 0) {
+                u32 v1 = rpos0 >> (LOGR - B1);
+                iR0 = p.bitrev_digit ? brev_rt(v1, B1) : v1;
+            }
+            if (B2 > 0) {
+                u32 v2 = (rpos0 >> (LOGR - B1 - B2)) & ((1u << B2) - 1);
+                iR0 |= (p.bitrev_digit ? brev_rt(v2, B2) : v2) << B1;
+            }
+            constexpr int SH = B1 + B2;  // kappa of this field enters i_R shifted by SH
+            bool scaled = false;
+            if (p.has_outer) {
+                const u64 lower = tc.low_base + (u64)c * p.low_cs;
+                const u64 A = ((u64)iR0 * lower * p.outer_mult) & p.n_mask;
+                const u64 Bs = ((lower << SH) * p.outer_mult) & p.n_mask;
+                u64 t = tw_lookup(tb.tw_lo, tb.tw_hi, p.hi_len, A);
+                const u64 st = tw_lookup(tb.tw_lo, tb.tw_hi, p.hi_len, Bs);
+                static_for<0, RAD>([&](auto KAP) {
+                    constexpr int q = brev_c(decltype(KAP)::value, B);
+                    x[q] = mul(x[q], t);
+                    if constexpr (decltype(KAP)::value + 1 < RAD) t = mul(t, st);
+                });
+                scaled = true;
+            }
+            if (p.has_post) {
+                const u64 A = tc.out_base + (u64)c * p.out_cs + (u64)iR0 * p.out_rs;
+                u64 t = tw_lookup(tc.sc_lo, tc.sc_hi, p.hi_len, A);
+                static_for<0, RAD>([&](auto KAP) {
+                    constexpr int q = brev_c(decltype(KAP)::value, B);
+                    x[q] = mul(x[q], t);
+                    if constexpr (decltype(KAP)::value + 1 < RAD) t = mul(t, p.post_step);
+                });
+                scaled = true;
+            }
+            if (!scaled) {
+                static_for<0, RAD>([&](auto K) { x[K] = canon(x[K]); });
+            }
+        }
+        // natural digit: output kappa -> field value kappa; bit-reversed digit: -> brev(kappa),
+        // i.e. register index q -> field value q.
+        if (p.bitrev_digit) {
+            static_for<0, RAD>([&](auto Q) { sm[padi(i0 + ((u32)Q << f))] = x[Q]; });
+        } else {
+            static_for<0, RAD>([&](auto KAP) { sm[padi(i0 + ((u32)KAP << f))] = x[brev_c(decltype(KAP)::value, B)]; });
+        }
+    }
+    __syncthreads();
+}
+
+template <int LOGR>
+struct Steps {
+    static constexpr int N = LOGR <= 4 ? 1 : (LOGR <= 8 ? 2 : 3);
+    static constexpr int A = N == 1 ? LOGR : (N == 2 ? (LOGR + 1) / 2 : (LOGR + 2) / 3);
+    static constexpr int Bb = N == 1 ? 0 : (N == 2 ? LOGR - A : (LOGR - A + 1) / 2);
+    static constexpr int C = N == 3 ? LOGR - A - Bb : 0;
+};
+
+template <int LOGR, bool INV>
+__global__ void __launch_bounds__(256) ntt_pass_kernel(const PassParams p, const Tables tb, const u64 *__restrict__ in,
+                                                       u64 *__restrict__ out) {
+    extern __shared__ u64 sm[];
+    using S = Steps<LOGR>;
+    const u32 R = 1u << LOGR, W = 1u << p.log_w, T = R << p.log_w;
+    const u32 nthreads = blockDim.x, tid = threadIdx.x;
+
+    // ---- batch decode
+    const u32 b = blockIdx.y;
+    const u32 lane = b % p.lanes;
+    const u32 cos = (b / p.lanes) % p.ncos;
+    const u32 col = b / (p.lanes * p.ncos);
+    const u64 *src = in + (u64)col * p.in_col_stride + (u64)cos * p.in_cos_stride + lane;
+    u64 *dst = out + (u64)col * p.out_col_stride + (u64)cos * p.out_cos_stride + lane;
+
+    // ---- tile decode
+    TileCtx tc;
+    tc.in_base = tc.out_base = tc.low_base = 0;
+    {
+        u32 t = blockIdx.x;
+        for (u32 d = 0; d < p.ndims; d++) {
+            u32 idx = t % p.dims[d].ext;
+            t /= p.dims[d].ext;
+            tc.in_base += (u64)idx * p.dims[d].in_str;
+            tc.out_base += (u64)idx * p.dims[d].out_str;
+            tc.low_base += (u64)idx * p.dims[d].low_str;
+        }
+    }
+    tc.sc_lo = tb.sc_lo ? tb.sc_lo + (u64)cos * 4096 : nullptr;
+    tc.sc_hi = tb.sc_hi ? tb.sc_hi + (u64)cos * p.hi_len : nullptr;
+    tc.pre_step = (p.has_pre && tb.pre_step) ? tb.pre_step[cos] : 0;
+
+    // ---- global -> shared (coalesced along whichever tile dimension is contiguous)
+    const u32 es = p.estride;
+    if (p.in_r_fast) {
+        for (u32 i = tid; i < T; i += nthreads) {
+            u32 r = i & (R - 1), c = i >> LOGR;
+            sm[padi((r << p.log_w) + c)] = src[(tc.in_base + (u64)r * p.in_rs + (u64)c * p.in_cs) * es];
+        }
+    } else {
+        for (u32 i = tid; i < T; i += nthreads) {
+            u32 c = i & (W - 1), r = i >> p.log_w;
+            sm[padi(i)] = src[(tc.in_base + (u64)r * p.in_rs + (u64)c * p.in_cs) * es];
+        }
+    }
+    __syncthreads();
+
+    // ---- CTA-level sub-NTT
+    const int lw = p.log_w;
+    if constexpr (S::N == 1) {
+        do_step<S::A, INV, true, true, 0, 0, LOGR>(sm, p, tb, tc, lw, 0);
+    } else if constexpr (S::N == 2) {
+        do_step<S::A, INV, true, false, 0, 0, LOGR>(sm, p, tb, tc, lw + LOGR - S::A, LOGR - S::A);
+        do_step<S::Bb, INV, false, true, S::A, 0, LOGR>(sm, p, tb, tc, lw, 0);
+    } else {
+        do_step<S::A, INV, true, false, 0, 0, LOGR>(sm, p, tb, tc, lw + LOGR - S::A, LOGR - S::A);
+        do_step<S::Bb, INV, false, false, S::A, 0, LOGR>(sm, p, tb, tc, lw + S::C, S::C);
+        do_step<S::C, INV, false, true, S::A, S::Bb, LOGR>(sm, p, tb, tc, lw, 0);
+    }
+
+    // ---- shared -> global.  rho = output row (natural digit: i_R, stored at the digit-reversed
+    // position; bit-reversed digit: the position itself).
+    auto pos_of = [&](u32 rho) -> u32 {
+        if (p.bitrev_digit) return rho;
+        if (S::N == 1) return rho;
+        if (S::N == 2) return ((rho & ((1u << S::A) - 1)) << (LOGR - S::A)) | (rho >> S::A);
+        u32 k1 = rho & ((1u << S::A) - 1), k2 = (rho >> S::A) & ((1u << S::Bb) - 1), k3 = rho >> (S::A + S::Bb);
+        return (k1 << (LOGR - S::A)) | (k2 << S::C) | k3;
+    };
+    if (p.out_r_fast) {
+        for (u32 i = tid; i < T; i += nthreads) {
+            u32 rho = i & (R - 1), c = i >> LOGR;
+            dst[(tc.out_base + (u64)rho * p.out_rs + (u64)c * p.out_cs) * es] = sm[padi((pos_of(rho) << p.log_w) + c)];
+        }
+    } else {
+        for (u32 i = tid; i < T; i += nthreads) {
+            u32 c = i & (W - 1), rho = i >> p.log_w;
+            dst[(tc.out_base + (u64)rho * p.out_rs + (u64)c * p.out_cs) * es] = sm[padi((pos_of(rho) << p.log_w) + c)];
+        }
+    }
+}
+
+template <int LOGR>
+static void launch_t(const PassParams &p, const Tables &t, bool inverse, const u64 *in, u64 *out, unsigned ntiles,
+                     unsigned nbatch, cudaStream_t stream) {
+    const unsigned T = 1u << (LOGR + p.log_w);
+    const unsigned threads = T / kElemsPerThread;
+    const size_t smem = (size_t)(T + (T >> 4) + 1) * sizeof(u64);
+    dim3 grid(ntiles, nbatch);
+    if (inverse)
+        ntt_pass_kernel<LOGR, true><<<grid, threads, smem, stream>>>(p, t, in, out);
+    else
+        ntt_pass_kernel<LOGR, false><<<grid, threads, smem, stream>>>(p, t, in, out);
+}
+
+void launch_pass(const PassParams &p, const Tables &t, bool inverse, const u64 *in, u64 *out, unsigned ntiles,
+                 unsigned nbatch, cudaStream_t stream) {
+    switch (p.log_r) {
+#define MS_CASE(L) case L: launch_t<L>(p, t, inverse, in, out, ntiles, nbatch, stream); break;
+        MS_CASE(1) MS_CASE(2) MS_CASE(3) MS_CASE(4) MS_CASE(5) MS_CASE(6)
+        MS_CASE(7) MS_CASE(8) MS_CASE(9) MS_CASE(10) MS_CASE(11) MS_CASE(12)
+#undef MS_CASE
+        default: break;
+    }
+}
+
+void steps_of(int log_r, int out[3], int *nsteps) {
+    int n = log_r <= 4 ? 1 : (log_r <= 8 ? 2 : 3);
+    int a = n == 1 ? log_r : (n == 2 ? (log_r + 1) / 2 : (log_r + 2) / 3);
+    int b = n == 1 ? 0 : (n == 2 ? log_r - a : (log_r - a + 1) / 2);
+    int c = n == 3 ? log_r - a - b : 0;
+    out[0] = a; out[1] = b; out[2] = c;
+    *nsteps = n;
+}
+
+std::vector<int> choose_digits(unsigned log_n) {
+    std::vector<int> d;
+    if (log_n <= (unsigned)kTileLog) {
+        d.push_back((int)log_n);
+        return d;
+    }
+    unsigned m = (log_n + 7) / 8;
+    unsigned base = log_n / m, rem = log_n % m;
+    for (unsigned i = 0; i < m; i++) d.push_back((int)(base + (i < rem ? 1 : 0)));
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------
+// Definition-based kernel: out[i] = sum_j in[j] * (offset * g^i)^j  (forward), or its inverse
+// (in[j] evaluated at g^-i, scaled by n^-1 * offset^-i).  O(n) per thread.
+__global__ void ntt_naive_kernel(const u64 *__restrict__ in, u64 in_stride_words, u64 *__restrict__ out,
+                                 u64 out_stride_words, unsigned log_n, unsigned estride, unsigned lanes, bool inverse,
+                                 u64 root, u64 offset) {
+    const u64 n = 1ull << log_n;
+    const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned lane = blockIdx.y % lanes, col = blockIdx.y / lanes;
+    const u64 *src = in + (u64)col * in_stride_words + lane;
+    u64 *dst = out + (u64)col * out_stride_words + lane;
+    u64 acc = 0;
+    if (!inverse) {
+        u64 x = mul(offset, pow(root, i));
+        for (u64 j = n; j-- > 0;) acc = add(mul(acc, x), src[j * estride]);
+    } else {
+        u64 x = pow(inv(root), i);
+        for (u64 j = n; j-- > 0;) acc = add(mul(acc, x), src[j * estride]);
+        acc = mul(acc, mul(inv(to_mont(n)), pow(inv(offset), i)));
+    }
+    dst[i * estride] = acc;
+}
+
+void launch_naive(const u64 *in, u64 in_stride_words, u64 *out, u64 out_stride_words, unsigned log_n, unsigned estride,
+                  unsigned lanes, unsigned ncols, bool inverse, u64 root_mont, u64 offset_mont, cudaStream_t stream) {
+    const u64 n = 1ull << log_n;
+    unsigned threads = n < 128 ? (unsigned)n : 128;
+    dim3 grid((unsigned)((n + threads - 1) / threads), ncols * lanes);
+    ntt_naive_kernel<<<grid, threads, 0, stream>>>(in, in_stride_words, out, out_stride_words, log_n, estride, lanes,
+                                                   inverse, root_mont, offset_mont);
+}
+
+}  // namespace msntt

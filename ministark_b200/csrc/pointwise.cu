@@ -1,0 +1,217 @@
+// pointwise.cu — element-wise field stages.
+//
+// One CUDA kernel family covers the reference's 17 Metal templates / 58 instantiations
+// (gpu/src/metal/evaluation_shaders.h.metal:11-168, wrapped by 14 *Stage structs in
+// gpu/src/stage.rs): MulInto/MulAssign (+Const), AddInto/AddAssign (+Const), ConvertInto,
+// InverseInto/InPlace, ExpInto/InPlace, NegInto/InPlace, MulPow, FillBuff; operand fields
+// Fp x Fp, Fq3 x Fp, Fq3 x Fq3.  rhs is read at (i + shift) % n as in the reference.
+// Also Matrix::sum_columns (src/matrix.rs:322-394) as ONE pass over all columns instead of
+// one AddAssign dispatch per column.
+// These are streaming kernels (HBM bound): one element per thread, grid sized to cover n.
+#include "ctx.cuh"
+
+namespace ms {
+
+using gl::Fq3;
+
+template <int F>
+struct Elem;
+template <>
+struct Elem<1> {
+    typedef u64 T;
+    static __device__ __forceinline__ T load(const u64 *p, size_t i) { return p[i]; }
+    static __device__ __forceinline__ void store(u64 *p, size_t i, T v) { p[i] = v; }
+};
+template <>
+struct Elem<3> {
+    typedef Fq3 T;
+    static __device__ __forceinline__ T load(const u64 *p, size_t i) { return Fq3{p[3 * i], p[3 * i + 1], p[3 * i + 2]}; }
+    static __device__ __forceinline__ void store(u64 *p, size_t i, T v) {
+        p[3 * i] = v.c0; p[3 * i + 1] = v.c1; p[3 * i + 2] = v.c2;
+    }
+};
+
+__device__ __forceinline__ Fq3 lift(u64 a) { return gl::fq3(a); }
+__device__ __forceinline__ Fq3 lift(Fq3 a) { return a; }
+// mixed products pick the cheapest form
+__device__ __forceinline__ u64 fmul(u64 a, u64 b) { return gl::mul(a, b); }
+__device__ __forceinline__ Fq3 fmul(Fq3 a, u64 b) { return gl::mul(a, b); }
+__device__ __forceinline__ Fq3 fmul(u64 a, Fq3 b) { return gl::mul(b, a); }
+__device__ __forceinline__ Fq3 fmul(Fq3 a, Fq3 b) { return gl::mul(a, b); }
+__device__ __forceinline__ u64 fadd(u64 a, u64 b) { return gl::add(a, b); }
+__device__ __forceinline__ Fq3 fadd(Fq3 a, u64 b) { return Fq3{gl::add(a.c0, b), a.c1, a.c2}; }
+__device__ __forceinline__ Fq3 fadd(u64 a, Fq3 b) { return Fq3{gl::add(a, b.c0), b.c1, b.c2}; }
+__device__ __forceinline__ Fq3 fadd(Fq3 a, Fq3 b) { return gl::add(a, b); }
+__device__ __forceinline__ u64 fsub(u64 a, u64 b) { return gl::sub(a, b); }
+__device__ __forceinline__ Fq3 fsub(Fq3 a, u64 b) { return Fq3{gl::sub(a.c0, b), a.c1, a.c2}; }
+__device__ __forceinline__ Fq3 fsub(u64 a, Fq3 b) { return Fq3{gl::sub(a, b.c0), gl::neg(b.c1), gl::neg(b.c2)}; }
+__device__ __forceinline__ Fq3 fsub(Fq3 a, Fq3 b) { return gl::sub(a, b); }
+__device__ __forceinline__ u64 finv(u64 a) { return gl::inv(a); }
+__device__ __forceinline__ Fq3 finv(Fq3 a) { return gl::inv(a); }
+__device__ __forceinline__ u64 fpow(u64 a, u64 e) { return gl::pow(a, e); }
+__device__ __forceinline__ Fq3 fpow(Fq3 a, u64 e) { return gl::pow(a, e); }
+__device__ __forceinline__ u64 fneg(u64 a) { return gl::neg(a); }
+__device__ __forceinline__ Fq3 fneg(Fq3 a) { return gl::neg(a); }
+
+// store a value of type V into a destination of field DF (DF >= field of V, or V has c1=c2=0)
+template <int DF>
+__device__ __forceinline__ void put(u64 *dst, size_t i, u64 v) {
+    if (DF == 1) dst[i] = v;
+    else Elem<3>::store(dst, i, gl::fq3(v));
+}
+template <int DF>
+__device__ __forceinline__ void put(u64 *dst, size_t i, Fq3 v) {
+    if (DF == 1) dst[i] = v.c0;
+    else Elem<3>::store(dst, i, v);
+}
+
+template <int DF, int LF, int RF>
+__global__ void pointwise_kernel(int op, u64 *dst, const u64 *lhs, const u64 *rhs, size_t n, size_t shift, u64 exponent) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    typename Elem<LF>::T a = Elem<LF>::load(lhs, i);
+    size_t j = i + shift;
+    if (j >= n) j -= n;
+    switch (op) {
+        case MS_OP_MUL: put<DF>(dst, i, fmul(a, Elem<RF>::load(rhs, j))); break;
+        case MS_OP_ADD: put<DF>(dst, i, fadd(a, Elem<RF>::load(rhs, j))); break;
+        case MS_OP_SUB: put<DF>(dst, i, fsub(a, Elem<RF>::load(rhs, j))); break;
+        case MS_OP_MULPOW: put<DF>(dst, i, fmul(a, fpow(Elem<RF>::load(rhs, j), exponent))); break;
+        case MS_OP_CONVERT: put<DF>(dst, i, a); break;
+        case MS_OP_INV: put<DF>(dst, i, finv(a)); break;
+        case MS_OP_EXP: put<DF>(dst, i, fpow(a, exponent)); break;
+        case MS_OP_NEG: put<DF>(dst, i, fneg(a)); break;
+        default: break;
+    }
+}
+
+template <int DF, int LF, int CF>
+__global__ void pointwise_const_kernel(int op, u64 *dst, const u64 *lhs, u64 k0, u64 k1, u64 k2, size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    typename Elem<CF>::T k;
+    if constexpr (CF == 1) k = k0;
+    else k = Fq3{k0, k1, k2};
+    if (op == MS_OP_FILL) {
+        put<DF>(dst, i, k);
+        return;
+    }
+    typename Elem<LF>::T a = Elem<LF>::load(lhs, i);
+    switch (op) {
+        case MS_OP_MUL: put<DF>(dst, i, fmul(a, k)); break;
+        case MS_OP_ADD: put<DF>(dst, i, fadd(a, k)); break;
+        case MS_OP_SUB: put<DF>(dst, i, fsub(a, k)); break;
+        default: break;
+    }
+}
+
+__global__ void sum_columns_kernel(const u64 *cols, size_t col_stride_words, unsigned ncols, size_t nwords, u64 *acc) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    u64 s = 0;
+    for (unsigned c = 0; c < ncols; c++) s = gl::add(s, cols[(size_t)c * col_stride_words + i]);
+    acc[i] = s;
+}
+
+}  // namespace ms
+
+using namespace ms;
+
+extern "C" {
+
+int ms_pointwise(ms_ctx *c, int op, int df, void *dst, int lf, const void *lhs, int rf, const void *rhs, size_t n,
+                 size_t shift, uint64_t exponent) {
+    if (!c || !dst || !lhs) return MS_ERR_INVALID;
+    const bool binary = (op == MS_OP_MUL || op == MS_OP_ADD || op == MS_OP_SUB || op == MS_OP_MULPOW);
+    const bool unary = (op == MS_OP_CONVERT || op == MS_OP_INV || op == MS_OP_EXP || op == MS_OP_NEG);
+    if (!binary && !unary) return fail(c, MS_ERR_INVALID, "ms_pointwise: unknown op %d", op);
+    if ((df != 1 && df != 3) || (lf != 1 && lf != 3)) return fail(c, MS_ERR_INVALID, "ms_pointwise: bad field id");
+    if (binary && (!rhs || (rf != 1 && rf != 3))) return fail(c, MS_ERR_INVALID, "ms_pointwise: binary op needs rhs");
+    if (!binary) rf = 1;
+    const int res_field = (lf == 3 || (binary && rf == 3)) ? 3 : 1;
+    if (df < res_field) return fail(c, MS_ERR_INVALID, "ms_pointwise: destination field too small for the result");
+    if (n == 0) return MS_OK;
+    if (shift >= n) shift %= n;
+    const bool alias = (dst == lhs);
+    Staged L(c, lhs, n * lf * 8, true, alias);
+    if (L.rc) return L.rc;
+    Staged Rr(c, binary ? rhs : nullptr, binary ? n * rf * 8 : 0, true, false);
+    if (Rr.rc) return Rr.rc;
+    Staged D(c, alias ? nullptr : dst, alias ? 0 : n * df * 8, false, true);
+    if (D.rc) return D.rc;
+    u64 *d = alias ? L.as<u64>() : D.as<u64>();
+    const u64 *l = L.as<u64>(), *r = binary ? Rr.as<u64>() : l;
+    if (alias && df != lf) return fail(c, MS_ERR_INVALID, "ms_pointwise: in-place form needs dst field == lhs field");
+    // in-place with a shifted rhs that aliases dst would race (the reference never does that)
+    const unsigned threads = 256, blocks = (unsigned)((n + threads - 1) / threads);
+#define MS_PW(DF, LF, RF) pointwise_kernel<DF, LF, RF><<<blocks, threads, 0, c->stream>>>(op, d, l, r, n, shift, exponent)
+    if (df == 1) MS_PW(1, 1, 1);
+    else if (lf == 1 && rf == 1) MS_PW(3, 1, 1);
+    else if (lf == 1 && rf == 3) MS_PW(3, 1, 3);
+    else if (lf == 3 && rf == 1) MS_PW(3, 3, 1);
+    else MS_PW(3, 3, 3);
+#undef MS_PW
+    c->launches++;
+    MS_CHECK_LAUNCH(c);
+    int rc;
+    if ((rc = L.finish())) return rc;
+    if ((rc = Rr.finish())) return rc;
+    return D.finish();
+}
+
+int ms_pointwise_const(ms_ctx *c, int op, int df, void *dst, int lf, const void *lhs, int cf, const uint64_t *k, size_t n) {
+    if (!c || !dst || !k) return MS_ERR_INVALID;
+    if (op != MS_OP_MUL && op != MS_OP_ADD && op != MS_OP_SUB && op != MS_OP_FILL)
+        return fail(c, MS_ERR_INVALID, "ms_pointwise_const: unknown op %d", op);
+    if ((df != 1 && df != 3) || (cf != 1 && cf != 3)) return fail(c, MS_ERR_INVALID, "ms_pointwise_const: bad field id");
+    if (op == MS_OP_FILL) { lf = 1; lhs = nullptr; }
+    else if (!lhs || (lf != 1 && lf != 3)) return fail(c, MS_ERR_INVALID, "ms_pointwise_const: needs lhs");
+    const int res_field = (lf == 3 || cf == 3) ? 3 : 1;
+    if (df < res_field) return fail(c, MS_ERR_INVALID, "ms_pointwise_const: destination field too small");
+    if (n == 0) return MS_OK;
+    u64 kk[3] = {0, 0, 0};
+    if (is_device_ptr(k)) MS_CUDA(c, cudaMemcpy(kk, k, cf * 8, cudaMemcpyDeviceToHost));
+    else for (int i = 0; i < cf; i++) kk[i] = k[i];
+    const bool alias = (dst == lhs);
+    if (alias && df != lf) return fail(c, MS_ERR_INVALID, "ms_pointwise_const: in-place form needs dst field == lhs field");
+    Staged L(c, lhs, lhs ? n * lf * 8 : 0, true, alias);
+    if (L.rc) return L.rc;
+    Staged D(c, alias ? nullptr : dst, alias ? 0 : n * df * 8, false, true);
+    if (D.rc) return D.rc;
+    u64 *d = alias ? L.as<u64>() : D.as<u64>();
+    const u64 *l = L.as<u64>();
+    const unsigned threads = 256, blocks = (unsigned)((n + threads - 1) / threads);
+#define MS_PC(DF, LF, CF) pointwise_const_kernel<DF, LF, CF><<<blocks, threads, 0, c->stream>>>(op, d, l, kk[0], kk[1], kk[2], n)
+    if (df == 1) MS_PC(1, 1, 1);
+    else if (lf == 1 && cf == 1) MS_PC(3, 1, 1);
+    else if (lf == 1 && cf == 3) MS_PC(3, 1, 3);
+    else if (lf == 3 && cf == 1) MS_PC(3, 3, 1);
+    else MS_PC(3, 3, 3);
+#undef MS_PC
+    c->launches++;
+    MS_CHECK_LAUNCH(c);
+    int rc;
+    if ((rc = L.finish())) return rc;
+    return D.finish();
+}
+
+int ms_sum_columns(ms_ctx *c, int field, const void *cols, size_t col_stride_elems, unsigned ncols, size_t n, void *acc) {
+    if (!c || !cols || !acc) return MS_ERR_INVALID;
+    if (field != 1 && field != 3) return fail(c, MS_ERR_INVALID, "ms_sum_columns: bad field id");
+    if (ncols > 1 && col_stride_elems < n) return fail(c, MS_ERR_INVALID, "ms_sum_columns: stride < n");
+    if (n == 0) return MS_OK;
+    Staged in(c, cols, ncols ? ((size_t)(ncols - 1) * col_stride_elems + n) * field * 8 : 0, true, false);
+    if (in.rc) return in.rc;
+    Staged out(c, acc, n * field * 8, false, true);
+    if (out.rc) return out.rc;
+    const size_t nwords = n * field;
+    sum_columns_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, c->stream>>>(in.as<u64>(), col_stride_elems * field, ncols,
+                                                                                 nwords, out.as<u64>());
+    c->launches++;
+    MS_CHECK_LAUNCH(c);
+    int rc;
+    if ((rc = in.finish())) return rc;
+    return out.finish();
+}
+
+}  // extern "C"

@@ -1,0 +1,40 @@
+"""CPU-only: the C-ABI library builds, loads, and exports every symbol include/ministark_b200.h
+declares.  No compute calls (there is no GPU here)."""
+import ctypes
+import os
+
+from ministark_b200 import _lib
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _lib.header_symbols()
+    assert len(declared) >= 25
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    # every bound signature is declared in the header and vice versa
+    assert sorted(_lib._SIGS) == declared
+
+
+def test_version_and_no_device_is_an_error_not_a_fallback():
+    lib = _lib.load()
+    assert b"sm_100a" in lib.ms_version()
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        h = ctypes.c_void_p()
+        rc = lib.ms_ctx_create(0, ctypes.byref(h))
+        assert rc != 0 and not h.value  # fails loudly: MS_ERR_NODEVICE, no CPU path
+
+
+def test_product_never_imports_the_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dirpath, _, files in os.walk(os.path.join(root, "ministark_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("no CPU fallback and nothing from oracle/ is ever imported", ""), f
