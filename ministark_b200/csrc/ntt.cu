@@ -294,7 +294,7 @@ __global__ void ntt_naive_kernel(const u64 *__restrict__ in, u64 in_stride_words
         u64 x = mul(offset, pow(root, i));
         for (u64 j = n; j-- > 0;) acc = add(mul(acc, x), src[j * estride]);
     } else {
-        u64 x = pow(inv(root), i);
+        u64 x = pow(root, i);  // `root` is already the inverse root for inverse plans
         for (u64 j = n; j-- > 0;) acc = add(mul(acc, x), src[j * estride]);
         acc = mul(acc, mul(inv(to_mont(n)), pow(inv(offset), i)));
     }
