@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE config 3: synthetic 2^24-row x 32-column Fp trace ->
+iNTT -> coset LDE (blowup 8, bit-reversed rows) -> SHA-256 Merkle commit -> constraint
+evaluation over the ce domain, on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps K --warmup W            (N>1: launched by torchrun)
+    python bench.py --impl reference ...                     CPU arm: the restated reference CPU
+                                                             path (oracle/) on a bounded sample
+
+Prints ONE JSON line (rank 0).  metric = NTT field-ops/s: the field operations of the step's
+transforms (1.5 * N * log2 N per N-point transform) divided by the time of the
+WHOLE step (transforms + Merkle commit + constraint evaluation), so it moves with "prover
+seconds for a 2^24 trace".  See DESIGN.md §Measurement for every key.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG_N_DEFAULT = 24
+NCOLS_DEFAULT = 32
+LOG_BLOWUP = 3
+L2_BYTES = 126 << 20
+
+
+def field_ops(log_n, log_b, ncols):
+    n, N = 1 << log_n, 1 << (log_n + log_b)
+    return ncols * 1.5 * (n * log_n + N * (log_n + log_b))
+
+
+def algorithmic_bytes(log_n, log_b, ncols):
+    """SURVEY.md §8d per phase, 8-byte Fp elements."""
+    n, N = 1 << log_n, 1 << (log_n + log_b)
+    return {
+        "intt": 2 * 8 * n * ncols,
+        "lde": (8 * n + 8 * N) * ncols,
+        "leaf_hash": (8 * ncols + 32) * N,
+        "merkle_nodes": 96 * (N - 1),
+        "constraint_eval": ((ncols + 1) * 8 + 8) * n,
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 7:
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(self.rows), "reasons": sorted(reasons)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """per-launch DRAM bytes of the dominant kernel from the committed ncu summary, or None"""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            pass
+    return None
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_sample(log_n, ncols, log_b, steps=1):
+    """The restated reference CPU path (oracle/gl_oracle.c, all host threads) on a bounded sample:
+    same pipeline, 2^log_n rows.  Returns (seconds per step, field-ops/s, threads, root)."""
+    from oracle import oracle as orc
+    from oracle import synth_oracle
+    threads = orc.num_threads()
+    trace = orc.rand_matrix(ncols, 1 << log_n, 1, seed=3000)
+    best = None
+    root = None
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        polys = orc.ntt(trace, 1, log_n, inverse=True)
+        lde = orc.lde(polys, 1, log_n, log_b, orc.generator(), bitrev=True)
+        nodes = orc.merkle_nodes(orc.hash_rows(lde, 1))
+        synth_oracle.constraint_eval(orc, lde, log_n, log_b, ncols)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        root = nodes[1].tobytes()
+    return best, field_ops(log_n, log_b, ncols) / best, threads, root
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    log_n = args.cpu_log_n
+    t0 = time.perf_counter()
+    for _ in range(args.warmup and 1):
+        cpu_sample(log_n, args.ncols, LOG_BLOWUP)
+    times = []
+    val = 0.0
+    threads = 1
+    for _ in range(args.steps):
+        dt, val_i, threads, _ = cpu_sample(log_n, args.ncols, LOG_BLOWUP)
+        times.append(dt)
+    ms = 1000 * sum(times) / len(times)
+    val = field_ops(log_n, LOG_BLOWUP, args.ncols) / (ms / 1000)
+    sample = (f"2^{log_n}-row x {args.ncols}-col trace (1/{1 << (args.log_n - log_n)} of the rows), all phases, "
+              f"{threads} host threads, oracle/gl_oracle.c restated reference CPU path")
+    print(json.dumps({
+        "impl": "reference", "metric": "ntt_field_ops_per_s", "value": val, "unit": "field-ops/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": val, "unit": "field-ops/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "field-ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }))
+
+
+def workload_config(args):
+    return {"workload": f"config3: synthetic 2^{args.log_n}-row x {args.ncols}-col Fp trace, iNTT + coset LDE x{1 << LOG_BLOWUP} "
+                        "(bit-reversed) + SHA-256 Merkle commit + constraint eval (32 degree-2 transition constraints, ce_blowup 1)",
+            "log_n": args.log_n, "ncols": args.ncols, "blowup": 1 << LOG_BLOWUP,
+            "l2_policy": "inputs (>= 4 GiB per phase) far exceed the 126 MB L2; no explicit flush",
+            "parallelism": f"{args.gpus} x independent trace shard (columns/job per GPU), no data-path collective"}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import ministark_b200 as ms
+    from ministark_b200 import synth_air
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    log_n, log_b, ncols = args.log_n, LOG_BLOWUP, args.ncols
+    n, N = 1 << log_n, 1 << (log_n + log_b)
+    stream = torch.cuda.current_stream()
+    ctx = ms.Context(local, stream=stream.cuda_stream)
+
+    dev = torch.device("cuda", local)
+    trace = torch.empty((ncols, n), dtype=torch.int64, device=dev)
+    polys = torch.empty((ncols, n), dtype=torch.int64, device=dev)
+    lde = torch.empty((ncols, N), dtype=torch.int64, device=dev)
+    leaves = torch.empty((N, 4), dtype=torch.int64, device=dev)
+    nodes = torch.empty((N, 4), dtype=torch.int64, device=dev)
+    ce_out = torch.empty(n, dtype=torch.int64, device=dev)
+    ctx.fill_random(trace, ncols * n, 3000 + rank)
+    evaluator = synth_air.GpuConstraintEval(ctx, log_n, log_b, ncols, dev)
+    host_trace = None
+
+    def step(from_host=False):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        ev[0].record()
+        if from_host:
+            trace.copy_(host_trace, non_blocking=True)
+        ev[1].record()
+        ctx.ntt_batch_to(trace, polys, ms.FP, log_n, ncols, inverse=True)
+        ev[2].record()
+        ctx.lde_batch(polys, lde, ms.FP, log_n, log_b, ncols, offset=ms.GENERATOR, bitrev=True)
+        ev[3].record()
+        root = ctx.merkle_commit(lde, ms.FP, N, ncols, leaves=leaves, nodes=nodes)   # D2H of the 32-byte root
+        ev[4].record()
+        evaluator.run(lde, ce_out)
+        ev[5].record()
+        return ev, root
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = ctx.launches
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    evs = []
+    root = None
+    for _ in range(args.steps):
+        e, root = step()
+        evs.append(e)
+    t_end.record()
+    barrier()
+    launches = ctx.launches - l0
+    clk = clocks.stop()
+    total_ms = t_start.elapsed_time(t_end)
+    names = ["h2d", "intt", "lde", "merkle", "constraint_eval"]
+    phase_ms = {nm: sum(e[i].elapsed_time(e[i + 1]) for e in evs) / args.steps for i, nm in enumerate(names)}
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    ops = field_ops(log_n, log_b, ncols) * world
+    value = ops / (ms_per_step / 1000)
+
+    # ---- end to end through the public API with HOST buffers: pinned host trace -> H2D -> pipeline
+    #      -> D2H of the Merkle root and of the constraint-evaluation column
+    host_trace = torch.empty((ncols, n), dtype=torch.int64, pin_memory=True)
+    host_trace.copy_(trace)
+    host_ce = torch.empty(n, dtype=torch.int64, pin_memory=True)
+    e2e_steps = max(1, min(args.steps, 3))
+    step(True)
+    barrier()
+    t_start.record()
+    for _ in range(e2e_steps):
+        step(True)
+        host_ce.copy_(ce_out, non_blocking=True)
+    t_end.record()
+    barrier()
+    e2e_ms = t_start.elapsed_time(t_end) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = ops / (e2e_ms / 1000)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel family (the NTT pass kernel, msntt::ntt_pass_kernel): the LDE
+    #      is 3 launches of it; achieved = algorithmic LDE bytes / device time of those launches.
+    alg = algorithmic_bytes(log_n, log_b, ncols)
+    peak, peak_src = measured_peak_hbm()
+    lde_gbs = alg["lde"] / (phase_ms["lde"] / 1000) / 1e9
+    traffic = ncu_traffic()
+    roofline = {"kernel": "msntt::ntt_pass_kernel (LDE: 3 launches)", "bound": "hbm", "achieved": lde_gbs, "peak": peak,
+                "unit": "GB/s", "frac": lde_gbs / peak, "peak_source": peak_src,
+                "traffic": traffic.get("lde_dram_bytes_per_launch") if traffic else None,
+                "algorithmic_bytes": alg["lde"], "launch_ms_sum": phase_ms["lde"],
+                "per_phase_GBps": {k: (alg[k2] / (phase_ms[k] / 1000) / 1e9) for k, k2 in
+                                   (("intt", "intt"), ("lde", "lde"), ("constraint_eval", "constraint_eval"))},
+                "merkle_GBps": (alg["leaf_hash"] + alg["merkle_nodes"]) / (phase_ms["merkle"] / 1000) / 1e9,
+                "note": "integer-ALU bound (64-bit modular arithmetic / SHA-256), see DESIGN.md"}
+
+    # ---- CPU baseline: restated reference CPU path on a bounded sample, host cores of this box
+    cpu = None
+    if not args.no_cpu:
+        dt, cval, threads, _ = cpu_sample(args.cpu_log_n, ncols, log_b)
+        cpu = {"value": cval, "unit": "field-ops/s", "cores": threads, "kind": "port", "seconds": dt,
+               "sample": f"2^{args.cpu_log_n}-row x {ncols}-col trace (1/{1 << (log_n - args.cpu_log_n)} of the rows), all phases, "
+                         "oracle/gl_oracle.c (restated reference CPU path, OpenMP over all host threads)"}
+
+    out = {
+        "metric": "ntt_field_ops_per_s", "value": value, "unit": "field-ops/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args),
+        "prover_s": ms_per_step / 1000, "phase_ms": phase_ms, "gpu_launches": launches, "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": "field-ops/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": ncols * n * 8, "d2h_bytes_per_step": 32 + n * 8},
+        "roofline": roofline, "cpu_baseline": cpu, "merkle_root": root.hex() if root else None,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", type=int, default=LOG_N_DEFAULT)
+    ap.add_argument("--ncols", type=int, default=NCOLS_DEFAULT)
+    ap.add_argument("--cpu-log-n", type=int, default=20, help="rows of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.cpu_log_n = min(args.cpu_log_n, args.log_n)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -94,6 +94,10 @@ int ms_ntt_plan_destroy(ms_ntt_plan *plan);
  *      into_bit_reversed_evaluations} (src/matrix.rs:101-251) ---- */
 int ms_ntt_batch(ms_ctx *ctx, int field, void *data, size_t col_stride_elems, unsigned ncols,
                  unsigned log_n, int direction, uint64_t offset_mont);
+/* out-of-place form (Matrix::interpolate = clone + into_polynomials, src/matrix.rs:157-163, without
+ * the clone): src is left untouched; src == dst is allowed. */
+int ms_ntt_batch_to(ms_ctx *ctx, int field, const void *src, size_t src_stride_elems, void *dst,
+                    size_t dst_stride_elems, unsigned ncols, unsigned log_n, int direction, uint64_t offset_mont);
 /* coefficients (2^log_n per column) -> evaluations over offset*<g_N>, N = 2^(log_n+log_blowup),
  * bit-reversed row order when bitrev_out != 0 (no zero padding, no separate bit-reverse pass). */
 int ms_lde_batch(ms_ctx *ctx, int field, const void *coeffs, size_t in_stride_elems, void *evals,
@@ -131,6 +135,19 @@ int ms_merkle_commit_sha256(ms_ctx *ctx, int field, const void *cols, size_t col
  * Equals bit_reverse ∘ NTT ∘ fold ∘ (·ff) ∘ iNTT ∘ bit_reverse of the reference, in one pass. */
 int ms_fri_fold(ms_ctx *ctx, int field, const void *evals, unsigned log_n, unsigned log_ff,
                 uint64_t offset_mont, const uint64_t *alpha, void *out);
+
+/* ---- constraint evaluation: AirConfig::eval_constraint -> eval_cpu::eval (src/air.rs:86-128,
+ *      src/eval_cpu.rs:33-150; dead GPU twin src/eval_gpu.rs:46-131) as ONE fused kernel ----
+ * program: nprog x 4 uint32 words, the linear form of the composition-constraint DAG produced by
+ * ministark_b200/expr.py::compile_program (opcodes in csrc/eval.cu); consts: nconsts x 3 Montgomery
+ * words.  base_cols: nbase Fp columns, ext_cols: next columns of `fq_field` elements, each holding the
+ * M = 2^log_m evaluations over the ce coset offset*<g_M> — in natural order, or (trace_bitrev != 0) as
+ * the first M entries of a bit-reversed LDE column (what src/prover.rs:86-91 un-permutes on the CPU).
+ * out: M elements of fq_field, natural order (one Fq value per ce-domain point). */
+int ms_eval_constraints(ms_ctx *ctx, const uint32_t *program, unsigned nprog, const uint64_t *consts,
+                        unsigned nconsts, const void *base_cols, size_t base_stride_elems, unsigned nbase,
+                        const void *ext_cols, size_t ext_stride_elems, unsigned next, int fq_field,
+                        unsigned log_m, uint64_t offset_mont, int trace_bitrev, void *out);
 
 /* ---- synthetic data: splitmix64, reject >= p, store x*2^64 mod p ---- */
 int ms_fill_random(ms_ctx *ctx, void *dst, size_t nwords, uint64_t seed);

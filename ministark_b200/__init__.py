@@ -113,6 +113,13 @@ class Context:
         self._ck(self.lib.ms_ntt_batch(self.h, field, _ptr(data), col_stride, ncols, log_n,
                                        INVERSE if inverse else FORWARD, offset))
 
+    def ntt_batch_to(self, src, dst, field, log_n, ncols=1, src_stride=None, dst_stride=None, inverse=False,
+                     offset=ONE):
+        src_stride = (1 << log_n) if src_stride is None else src_stride
+        dst_stride = (1 << log_n) if dst_stride is None else dst_stride
+        self._ck(self.lib.ms_ntt_batch_to(self.h, field, _ptr(src), src_stride, _ptr(dst), dst_stride, ncols, log_n,
+                                          INVERSE if inverse else FORWARD, offset))
+
     def lde_batch(self, coeffs, evals, field, log_n, log_blowup, ncols=1, in_stride=None, out_stride=None,
                   offset=GENERATOR, bitrev=True):
         in_stride = (1 << log_n) if in_stride is None else in_stride
@@ -158,6 +165,17 @@ class Context:
     def fri_fold(self, evals, out, field, log_n, log_ff, alpha, offset=ONE):
         a = np.ascontiguousarray(alpha, dtype=np.uint64)
         self._ck(self.lib.ms_fri_fold(self.h, field, _ptr(evals), log_n, log_ff, offset, a.ctypes.data, _ptr(out)))
+
+    # ---- constraint evaluation
+    def eval_constraints(self, program, out, log_m, base_cols=None, nbase=0, base_stride=None, ext_cols=None, next_=0,
+                         ext_stride=None, fq_field=FP, offset=GENERATOR, trace_bitrev=False):
+        """AirConfig::eval_constraint (src/air.rs:86-128): `program` from expr.compile_program."""
+        m = 1 << log_m
+        self._ck(self.lib.ms_eval_constraints(
+            self.h, program.code.ctypes.data, len(program), program.consts.ctypes.data, program.consts.shape[0],
+            _ptr(base_cols), m if base_stride is None else base_stride, nbase,
+            _ptr(ext_cols), m if ext_stride is None else ext_stride, next_, fq_field, log_m, offset,
+            int(trace_bitrev), _ptr(out)))
 
     def fill_random(self, dst, nwords, seed):
         self._ck(self.lib.ms_fill_random(self.h, _ptr(dst), nwords, seed))

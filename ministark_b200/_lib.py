@@ -34,6 +34,7 @@ _SIGS = {
     "ms_ntt_execute": (ci, [vp]),
     "ms_ntt_plan_destroy": (ci, [vp]),
     "ms_ntt_batch": (ci, [vp, ci, vp, sz, ui, ui, ci, u64]),
+    "ms_ntt_batch_to": (ci, [vp, ci, vp, sz, vp, sz, ui, ui, ci, u64]),
     "ms_lde_batch": (ci, [vp, ci, vp, sz, vp, sz, ui, ui, ui, u64, ci]),
     "ms_bit_reverse": (ci, [vp, ci, vp, sz, ui, ui]),
     "ms_pointwise": (ci, [vp, ci, ci, vp, ci, vp, ci, vp, sz, sz, u64]),
@@ -43,6 +44,7 @@ _SIGS = {
     "ms_merkle_nodes_sha256": (ci, [vp, vp, sz, vp]),
     "ms_merkle_commit_sha256": (ci, [vp, ci, vp, sz, ui, sz, vp, vp, vp]),
     "ms_fri_fold": (ci, [vp, ci, vp, ui, ui, u64, vp, vp]),
+    "ms_eval_constraints": (ci, [vp, vp, ui, vp, ui, vp, sz, ui, vp, sz, ui, ci, ui, u64, ci, vp]),
     "ms_fill_random": (ci, [vp, vp, sz, u64]),
 }
 

@@ -64,15 +64,11 @@ int ntt_get_plan(ms_ctx *c, const NttJob &job, std::shared_ptr<NttPlanDev> *out)
     u64 root = root_of_unity(log_n);
     if (job.inverse) root = gl::inv(root);
     P->root = root;
-    if (log_n < 4) {
-        P->naive = true;
-        c->plans[key] = P;
-        *out = P;
-        return MS_OK;
-    }
+    P->naive = log_n < 4;
 
     // ---- digits and strides
-    std::vector<int> d = msntt::choose_digits(log_n);
+    std::vector<int> d;
+    if (!P->naive) d = msntt::choose_digits(log_n);
     const int m = (int)d.size();
     std::vector<u64> S(m), Pw(m);
     {
@@ -81,8 +77,8 @@ int ntt_get_plan(ms_ctx *c, const NttJob &job, std::shared_ptr<NttPlanDev> *out)
         u64 p = 1;
         for (int l = 0; l < m; l++) { Pw[l] = p; p <<= d[l]; }
     }
-    const bool has_pre = !job.inverse && (job.offset != gl::ONE || P->ncos > 1);
-    const bool has_post = job.inverse;
+    const bool has_pre = !P->naive && !job.inverse && (job.offset != gl::ONE || P->ncos > 1);
+    const bool has_post = !P->naive && job.inverse;
     const u32 hi_len = (u32)std::max<u64>(1, N >> 12);
 
     for (int k = 0; k < m; k++) {
@@ -187,7 +183,7 @@ int ntt_get_plan(ms_ctx *c, const NttJob &job, std::shared_ptr<NttPlanDev> *out)
             }
         }
     }
-    P->passes.back().post_step = post_step;
+    if (!P->passes.empty()) P->passes.back().post_step = post_step;
     cudaError_t e = cudaMalloc(&P->dev, h.size() * 8);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -205,6 +201,16 @@ int ntt_get_plan(ms_ctx *c, const NttJob &job, std::shared_ptr<NttPlanDev> *out)
     }
     c->plans[key] = P;
     *out = P;
+    return MS_OK;
+}
+
+int ntt_plan_tables(ms_ctx *c, unsigned log_n, const u64 **tw_lo, const u64 **tw_hi, u32 *hi_len) {
+    NttJob job{MS_FIELD_FP, log_n, false, false, 0, gl::ONE};
+    std::shared_ptr<NttPlanDev> P;
+    if (int rc = ntt_get_plan(c, job, &P)) return rc;
+    *tw_lo = P->tb.tw_lo;
+    *tw_hi = P->tb.tw_hi;
+    *hi_len = (u32)std::max<u64>(1, P->N >> 12);
     return MS_OK;
 }
 
@@ -381,6 +387,29 @@ int ms_ntt_batch(ms_ctx *c, int field, void *data, size_t col_stride_elems, unsi
     int rc = ntt_run(c, *P, d.as<u64>(), col_stride_elems * field, d.as<u64>(), col_stride_elems * field, ncols);
     if (rc) return rc;
     return d.finish();
+}
+
+int ms_ntt_batch_to(ms_ctx *c, int field, const void *src, size_t src_stride_elems, void *dst, size_t dst_stride_elems,
+                    unsigned ncols, unsigned log_n, int direction, uint64_t offset_mont) {
+    if (!c || !src || !dst) return MS_ERR_INVALID;
+    if (src == dst && src_stride_elems == dst_stride_elems)
+        return ms_ntt_batch(c, field, dst, dst_stride_elems, ncols, log_n, direction, offset_mont);
+    if (int rc = check_field(c, field)) return rc;
+    if (log_n > 32 || ncols == 0) return fail(c, MS_ERR_INVALID, "ms_ntt_batch_to: bad size");
+    if (offset_mont >= gl::P || offset_mont == 0) return fail(c, MS_ERR_INVALID, "offset must be a non-zero canonical word");
+    const size_t n = (size_t)1 << log_n;
+    if (ncols > 1 && (src_stride_elems < n || dst_stride_elems < n)) return fail(c, MS_ERR_INVALID, "ms_ntt_batch_to: stride < n");
+    NttJob job{field, log_n, direction == MS_NTT_INVERSE, false, 0, offset_mont};
+    std::shared_ptr<NttPlanDev> P;
+    if (int rc = ntt_get_plan(c, job, &P)) return rc;
+    Staged in(c, src, ((size_t)(ncols - 1) * src_stride_elems + n) * field * 8, true, false);
+    if (in.rc) return in.rc;
+    Staged out(c, dst, ((size_t)(ncols - 1) * dst_stride_elems + n) * field * 8, false, true);
+    if (out.rc) return out.rc;
+    int rc = ntt_run(c, *P, in.as<u64>(), src_stride_elems * field, out.as<u64>(), dst_stride_elems * field, ncols);
+    if (rc) return rc;
+    if ((rc = in.finish())) return rc;
+    return out.finish();
 }
 
 __global__ void pad_copy_kernel(const u64 *src, size_t src_stride, u64 *dst, size_t dst_stride, size_t n_words,

@@ -81,6 +81,8 @@ struct NttJob {
     u64 offset;             // Montgomery
 };
 int ntt_get_plan(ms_ctx *c, const NttJob &job, std::shared_ptr<NttPlanDev> *out);
+// two-level table of g_n^e (forward root of unity of order 2^log_n): e = 4096*e1 + e0
+int ntt_plan_tables(ms_ctx *c, unsigned log_n, const u64 **tw_lo, const u64 **tw_hi, u32 *hi_len);
 // run: natural mode: in == out allowed (uses scratch 0).  LDE mode: in -> out.
 int ntt_run(ms_ctx *c, NttPlanDev &plan, const u64 *in, size_t in_col_stride_words, u64 *out,
             size_t out_col_stride_words, unsigned ncols);

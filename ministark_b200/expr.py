@@ -1,0 +1,319 @@
+"""expr.py — symbolic constraint expressions and their compilation to the fused evaluator program.
+
+Host-side mirror of the reference's input format for constraint evaluation:
+    Expr<AlgebraicItem<FieldVariant<Fp, Fq>>>        src/expression.rs:31-39, src/constraints.rs:21-28
+with leaves  X | Constant | Challenge(i) | Hint(i) | Trace(column, row offset)  and nodes
+Neg | Add | Mul | Div | Pow(usize).  (Periodic columns are not supported yet; neither BASELINE
+AIR uses them.)
+
+The reference evaluates this DAG either with one GPU dispatch + barrier + full HBM round trip per
+node (eval_gpu.rs, disabled: src/air.rs:104-117) or on the CPU in 512-element chunks
+(eval_cpu.rs:76-150).  Here `compile_program` flattens the DAG once (hash-consed = the effect
+of reuse_shared_nodes, src/expression.rs:186-357; constant sub-expressions folded on the host;
+registers reused by liveness) into a linear typed program that ONE kernel (csrc/eval.cu) runs per
+evaluation point with all temporaries on chip.
+"""
+import numpy as np
+
+P = 2**64 - 2**32 + 1
+_R = 2**64
+_RINV = pow(_R, -1, P)
+
+FP, FQ = 0, 1  # value types: base field / extension ("Fq" is Fq3, or Fp itself when the AIR has Fq = Fp)
+
+# opcodes (must match csrc/eval.cu)
+OP_X, OP_CONST, OP_TRACE, OP_NEG, OP_ADD, OP_SUB, OP_MUL, OP_INV, OP_POW, OP_STORE = range(10)
+MAX_REGS = 48
+
+
+# ---- canonical-integer extension arithmetic for host-side constant folding (X^3 = 2)
+def _q(v):
+    return (v % P, 0, 0) if isinstance(v, int) else tuple(int(x) % P for x in v)
+
+
+def q_add(a, b):
+    return tuple((x + y) % P for x, y in zip(a, b))
+
+
+def q_neg(a):
+    return tuple((-x) % P for x in a)
+
+
+def q_mul(a, b):
+    pr = [0] * 5
+    for i in range(3):
+        for j in range(3):
+            pr[i + j] += a[i] * b[j]
+    return ((pr[0] + 2 * pr[3]) % P, (pr[1] + 2 * pr[4]) % P, pr[2] % P)
+
+
+def q_pow(a, e):
+    r = (1, 0, 0)
+    while e:
+        if e & 1:
+            r = q_mul(r, a)
+        a = q_mul(a, a)
+        e >>= 1
+    return r
+
+
+def q_inv(a):
+    return q_pow(a, P**3 - 2)
+
+
+class Expr:
+    """Immutable, hash-consed expression node.  Build with X(), Constant(), Challenge(), Hint(),
+    Trace() and the operators + - * / ** and unary -."""
+    _pool = {}
+    __slots__ = ("kind", "args", "_key")
+
+    def __new__(cls, kind, *args):
+        key = (kind,) + tuple(a._key if isinstance(a, Expr) else a for a in args)
+        node = cls._pool.get(key)
+        if node is None:
+            node = object.__new__(cls)
+            node.kind, node.args = kind, args
+            node._key = id(node)
+            cls._pool[key] = node
+        return node
+
+    @staticmethod
+    def _lift(v):
+        return v if isinstance(v, Expr) else Constant(v)
+
+    def __add__(self, o):
+        return Expr("add", self, Expr._lift(o))
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return Expr("add", self, Expr("neg", Expr._lift(o)))   # a - b = a + (-b), as the reference's Sub impl
+
+    def __rsub__(self, o):
+        return Expr._lift(o) - self
+
+    def __mul__(self, o):
+        return Expr("mul", self, Expr._lift(o))
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        return Expr("div", self, Expr._lift(o))
+
+    def __neg__(self):
+        return Expr("neg", self)
+
+    def __pow__(self, e):
+        return Expr("pow", self, int(e))
+
+    def to_tuple(self, memo=None):
+        """plain nested-tuple form (shared nodes stay shared) — the exchange format the tests hand
+        to the CPU oracle's evaluator."""
+        memo = {} if memo is None else memo
+        if id(self) not in memo:
+            memo[id(self)] = (self.kind,) + tuple(a.to_tuple(memo) if isinstance(a, Expr) else a for a in self.args)
+        return memo[id(self)]
+
+
+def X():
+    return Expr("x")
+
+
+def Constant(v, ext=False):
+    """canonical integer (base field) or 3-tuple of canonical integers (extension)"""
+    if isinstance(v, (tuple, list)):
+        return Expr("const", tuple(int(x) % P for x in v), True)
+    return Expr("const", (int(v) % P, 0, 0), bool(ext))
+
+
+def Challenge(i):
+    return Expr("chal", int(i))
+
+
+def Hint(i):
+    return Expr("hint", int(i))
+
+
+def Trace(col, offset=0):
+    return Expr("trace", int(col), int(offset))
+
+
+class Program:
+    def __init__(self, code, consts, nregs, out_is_q):
+        self.code = np.ascontiguousarray(code, dtype=np.uint32).reshape(-1, 4)
+        self.consts = np.ascontiguousarray(consts, dtype=np.uint64).reshape(-1, 3)
+        self.nregs, self.out_is_q = nregs, out_is_q
+
+    def __len__(self):
+        return self.code.shape[0]
+
+
+def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, log_ce=None):
+    """Flatten `expr` into the evaluator's linear program.
+
+    challenges / hints: extension elements as 3-tuples (or ints) of canonical integers, substituted
+    as constants exactly like eval_cpu.rs:116-118.  Trace(col, off) with col < num_base_cols reads a
+    base-field column, otherwise extension column col - num_base_cols; the row shift is
+    lde_step * off (eval_cpu.rs:119-123).  The result is always stored as an Fq element.
+    """
+    order, seen = [], set()
+
+    def visit(e):                      # iterative post-order (DAGs can be deep)
+        stack = [(e, False)]
+        while stack:
+            node, done = stack.pop()
+            if id(node) in seen and not done:
+                continue
+            if done:
+                order.append(node)
+                continue
+            seen.add(id(node))
+            stack.append((node, True))
+            for a in node.args:
+                if isinstance(a, Expr) and id(a) not in seen:
+                    stack.append((a, False))
+
+    # a / b  ->  a * inv(b) with inv(b) hash-consed, so a denominator shared by many constraints
+    # (the zerofier X^n - 1) is inverted once per point instead of once per Div node
+    rewritten = {}
+
+    def rewrite(e):
+        stack = [e]
+        while stack:
+            node = stack[-1]
+            if id(node) in rewritten:
+                stack.pop()
+                continue
+            kids = [a for a in node.args if isinstance(a, Expr)]
+            todo = [a for a in kids if id(a) not in rewritten]
+            if todo:
+                stack.extend(todo)
+                continue
+            args = tuple(rewritten[id(a)] if isinstance(a, Expr) else a for a in node.args)
+            if node.kind == "div":
+                rewritten[id(node)] = Expr("mul", args[0], Expr("inv", args[1]))
+            else:
+                rewritten[id(node)] = Expr(node.kind, *args)
+            stack.pop()
+        return rewritten[id(e)]
+
+    expr = rewrite(expr)
+    visit(expr)
+    # constant folding + typing
+    cval, typ = {}, {}
+    for nd in order:
+        k, a = nd.kind, nd.args
+        if k == "const":
+            cval[id(nd)] = a[0]
+            typ[id(nd)] = FQ if a[1] else FP
+        elif k == "chal":
+            cval[id(nd)] = _q(challenges[a[0]])
+            typ[id(nd)] = FQ
+        elif k == "hint":
+            cval[id(nd)] = _q(hints[a[0]])
+            typ[id(nd)] = FQ
+        elif k == "x":
+            typ[id(nd)] = FP
+        elif k == "trace":
+            typ[id(nd)] = FP if a[0] < num_base_cols else FQ
+        else:
+            kids = [x for x in a if isinstance(x, Expr)]
+            typ[id(nd)] = max(typ[id(x)] for x in kids)
+            if all(id(x) in cval for x in kids):
+                v = [cval[id(x)] for x in kids]
+                if k == "neg":
+                    cval[id(nd)] = q_neg(v[0])
+                elif k == "add":
+                    cval[id(nd)] = q_add(v[0], v[1])
+                elif k == "mul":
+                    cval[id(nd)] = q_mul(v[0], v[1])
+                elif k == "inv":
+                    cval[id(nd)] = q_inv(v[0])
+                elif k == "pow":
+                    cval[id(nd)] = q_pow(v[0], a[1])
+    # last use (for register reuse), skipping folded nodes
+    live_nodes = [nd for nd in order if id(nd) not in cval or nd is expr]
+    last_use = {}
+    for idx, nd in enumerate(live_nodes):
+        for x in nd.args:
+            if isinstance(x, Expr):
+                last_use[id(x)] = idx
+    consts, const_idx = [], {}
+
+    def const_slot(v):
+        if v not in const_idx:
+            const_idx[v] = len(consts)
+            consts.append([x * _R % P for x in v])      # Montgomery words
+        return const_idx[v]
+
+    code, reg_of, free, nregs = [], {}, [], 0
+
+    def alloc():
+        nonlocal nregs
+        if free:
+            return free.pop()
+        nregs += 1
+        if nregs > MAX_REGS:
+            raise ValueError(f"expression needs more than {MAX_REGS} live temporaries")
+        return nregs - 1
+
+    def operand(x):
+        """register holding node x (materialising folded constants on demand)"""
+        if id(x) in reg_of:
+            return reg_of[id(x)]
+        r = alloc()
+        code.append([OP_CONST | (typ[id(x)] << 8), r, const_slot(cval[id(x)]), 0])
+        reg_of[id(x)] = r
+        return r
+
+    def release(x, idx):
+        if last_use.get(id(x)) == idx and id(x) in reg_of:
+            free.append(reg_of.pop(id(x)))
+
+    for idx, nd in enumerate(live_nodes):
+        k, a = nd.kind, nd.args
+        t = typ[id(nd)]
+        if id(nd) in cval:            # the root itself is a constant
+            operand(nd)
+            continue
+        if k == "x":
+            r = alloc()
+            code.append([OP_X, r, 0, 0])
+        elif k == "trace":
+            col, off = a
+            is_q = col >= num_base_cols
+            shift = (lde_step * off)
+            if log_ce is not None:
+                shift %= (1 << log_ce)
+            r = alloc()
+            code.append([OP_TRACE | (int(is_q) << 8), r, col - (num_base_cols if is_q else 0), shift & 0xFFFFFFFF])
+        elif k == "neg":
+            ra = operand(a[0])
+            release(a[0], idx)
+            r = alloc()
+            code.append([OP_NEG | (typ[id(a[0])] << 8), r, ra, 0])
+        elif k in ("add", "mul"):
+            ra, rb = operand(a[0]), operand(a[1])
+            release(a[0], idx)
+            release(a[1], idx)
+            r = alloc()
+            op = OP_ADD if k == "add" else OP_MUL
+            code.append([op | (typ[id(a[0])] << 8) | (typ[id(a[1])] << 9), r, ra, rb])
+        elif k == "inv":
+            ra = operand(a[0])
+            release(a[0], idx)
+            r = alloc()
+            code.append([OP_INV | (typ[id(a[0])] << 8), r, ra, 0])
+        elif k == "pow":
+            ra = operand(a[0])
+            release(a[0], idx)
+            r = alloc()
+            if a[1] >= 2**32:
+                raise ValueError("exponent too large")
+            code.append([OP_POW | (typ[id(a[0])] << 8), r, ra, a[1]])
+        else:
+            raise ValueError(f"unsupported node {k}")
+        reg_of[id(nd)] = r
+    code.append([OP_STORE | (typ[id(expr)] << 8), 0, reg_of[id(expr)], 0])
+    return Program(np.array(code, dtype=np.uint32), np.array(consts if consts else [[0, 0, 0]], dtype=np.uint64),
+                   max(nregs, 1), typ[id(expr)] == FQ)
