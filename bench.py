@@ -190,7 +190,9 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     log_n, log_b, ncols = args.log_n, LOG_BLOWUP, args.ncols
     n, N = 1 << log_n, 1 << (log_n + log_b)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) torch stream: the library launches on it, torch events time on it
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
     ctx = ms.Context(local, stream=stream.cuda_stream)
 
     dev = torch.device("cuda", local)

@@ -24,10 +24,12 @@ struct NttPlanDev {
     u64 root = 0;
     std::vector<PassParams> passes;
     std::vector<unsigned> ntiles;
-    u64 *dev = nullptr;  // one allocation holding all tables
+    u64 *dev = nullptr;  // one allocation holding the small tables
+    std::vector<u64 *> big;  // full twiddle / scale tables
     msntt::Tables tb{};
     ~NttPlanDev() {
         if (dev) cudaFree(dev);
+        for (u64 *b : big) cudaFree(b);
     }
 };
 
@@ -199,6 +201,53 @@ int ntt_get_plan(ms_ctx *c, const NttJob &job, std::shared_ptr<NttPlanDev> *out)
         P->tb.sc_hi = P->tb.sc_lo + (size_t)P->ncos * lo_len;
         P->tb.pre_step = P->tb.sc_hi + (size_t)P->ncos * hi_len;
     }
+    // ---- full tables where they are affordable (one multiplication per element instead of the two of
+    //      the on-the-fly geometric progression); skipped silently if memory is short
+    {
+        auto try_alloc = [&](size_t words) -> u64 * {
+            u64 *d = nullptr;
+            if (cudaMalloc(&d, words * 8) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+            P->big.push_back(d);
+            return d;
+        };
+        const size_t kOuterMax = (size_t)64 << 20, kPreMax = (size_t)256 << 20;  // words (512 MiB / 2 GiB)
+        for (size_t k = 0; k < P->passes.size(); k++) {
+            PassParams &p = P->passes[k];
+            if (p.has_outer) {
+                const u64 R = 1ull << p.log_r, S = p.in_rs;
+                if (R * S <= kOuterMax) {
+                    if (u64 *d = try_alloc(R * S)) {
+                        msntt::build_outer_table(d, R, S, p.outer_mult, p.n_mask, P->tb.tw_lo, P->tb.tw_hi, hi_len, c->stream);
+                        c->launches++;
+                        p.outer_tab = d;
+                        p.outer_S = S;
+                    }
+                }
+            }
+            if (p.has_pre && (size_t)P->ncos * N <= kPreMax) {
+                if (u64 *d = try_alloc((size_t)P->ncos * N)) {
+                    for (unsigned q = 0; q < P->ncos; q++) {
+                        msntt::build_pow_table(d + (size_t)q * N, N, P->tb.sc_lo + (size_t)q * lo_len,
+                                               P->tb.sc_hi + (size_t)q * hi_len, hi_len, c->stream);
+                        c->launches++;
+                    }
+                    p.pre_tab = d;
+                    p.pre_cos_stride = N;
+                }
+            }
+            if (p.has_post && N <= kOuterMax) {
+                if (u64 *d = try_alloc(N)) {
+                    msntt::build_pow_table(d, N, P->tb.sc_lo, P->tb.sc_hi, hi_len, c->stream);
+                    c->launches++;
+                    p.post_tab = d;
+                }
+            }
+        }
+        MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
     c->plans[key] = P;
     *out = P;
     return MS_OK;
@@ -225,7 +274,11 @@ int ntt_run(ms_ctx *c, NttPlanDev &P, const u64 *in, size_t in_cs, u64 *out, siz
     const size_t col_words = (size_t)N * P.estride;
     const bool lde = P.job.bitrev_out;
     const size_t tmp_budget = (size_t)1 << 30;
-    unsigned max_cols = 65535u / (P.lanes * P.ncos);
+    unsigned max_tiles = 1;
+    for (unsigned t : P.ntiles) max_tiles = std::max(max_tiles, t);
+    // 1-D grid of ntiles * nbatch blocks (naive path: grid.y = columns * lanes)
+    unsigned max_cols = P.naive ? 65535u / P.lanes
+                                : (unsigned)std::max<u64>(1, (0x7FFFFFFFull / max_tiles) / (P.lanes * P.ncos));
     const int m = (int)P.passes.size();
     const bool need_tmp = P.naive ? (in == out) : (!lde && m >= 2);
     if (need_tmp) max_cols = (unsigned)std::max<size_t>(1, std::min<size_t>(max_cols, tmp_budget / (col_words * 8)));
@@ -278,7 +331,8 @@ int ntt_run(ms_ctx *c, NttPlanDev &P, const u64 *in, size_t in_cs, u64 *out, siz
                 p.in_col_stride = (k == 0) ? in_cs : col_words;
                 p.out_col_stride = (k == m - 1) ? out_cs : col_words;
             }
-            msntt::launch_pass(p, P.tb, P.job.inverse, pin, pout, P.ntiles[k], nc * P.lanes * P.ncos, c->stream);
+            p.nbatch = nc * P.lanes * P.ncos;
+            msntt::launch_pass(p, P.tb, P.job.inverse, pin, pout, P.ntiles[k], p.nbatch, c->stream);
             c->launches++;
             MS_CHECK_LAUNCH(c);
         }

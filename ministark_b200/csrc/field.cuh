@@ -54,34 +54,90 @@ GL_HD u64 neg(u64 a) { return a ? P - a : 0; }
 
 // ---- lazy arithmetic (any u64 in, any u64 out; value preserved mod p) ---------------
 // lc: second operand canonical (< p)  -> a single repair suffices.
-GL_HD u64 add_lc(u64 a, u64 t) {
+// ll: both operands arbitrary u64     -> up to two repairs.
+// Device versions are carry-chain PTX (5 / 5 / 9 / 8 SASS instructions instead of the 8 / 8 / 12 /
+// 12 the compiler makes of the portable forms below, which the host keeps).
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ u64 pack64(u32 lo, u32 hi) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void unpack64(u64 v, u32 &lo, u32 &hi) { asm("mov.b64 {%0,%1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+// s = a + t; on carry add eps = 2^32 - 1, i.e. low -= c, high += c - borrow
+__device__ __forceinline__ u64 add_lc(u64 a, u64 t) {
+    u32 a0, a1, t0, t1, s0, s1;
+    unpack64(a, a0, a1); unpack64(t, t0, t1);
+    asm("{\n\t.reg .u32 c;\n\tadd.cc.u32 %0, %2, %4;\n\taddc.cc.u32 %1, %3, %5;\n\taddc.u32 c, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, c;\n\tsubc.u32 %1, %1, 0;\n\tadd.u32 %1, %1, c;\n\t}"
+        : "=r"(s0), "=r"(s1) : "r"(a0), "r"(a1), "r"(t0), "r"(t1));
+    return pack64(s0, s1);
+}
+// d = a - t; on borrow subtract eps (m = 0xffffffff is eps as a low word)
+__device__ __forceinline__ u64 sub_lc(u64 a, u64 t) {
+    u32 a0, a1, t0, t1, s0, s1;
+    unpack64(a, a0, a1); unpack64(t, t0, t1);
+    asm("{\n\t.reg .u32 m;\n\tsub.cc.u32 %0, %2, %4;\n\tsubc.cc.u32 %1, %3, %5;\n\tsubc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\tsubc.u32 %1, %1, 0;\n\t}"
+        : "=r"(s0), "=r"(s1) : "r"(a0), "r"(a1), "r"(t0), "r"(t1));
+    return pack64(s0, s1);
+}
+__device__ __forceinline__ u64 add_ll(u64 a, u64 t) {
+    u32 a0, a1, t0, t1, s0, s1;
+    unpack64(a, a0, a1); unpack64(t, t0, t1);
+    asm("{\n\t.reg .u32 c;\n\tadd.cc.u32 %0, %2, %4;\n\taddc.cc.u32 %1, %3, %5;\n\taddc.u32 c, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, c;\n\tsubc.u32 %1, %1, 0;\n\tadd.cc.u32 %1, %1, c;\n\taddc.u32 c, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, c;\n\tsubc.u32 %1, %1, 0;\n\tadd.u32 %1, %1, c;\n\t}"
+        : "=r"(s0), "=r"(s1) : "r"(a0), "r"(a1), "r"(t0), "r"(t1));
+    return pack64(s0, s1);
+}
+__device__ __forceinline__ u64 sub_ll(u64 a, u64 t) {
+    u32 a0, a1, t0, t1, s0, s1;
+    unpack64(a, a0, a1); unpack64(t, t0, t1);
+    asm("{\n\t.reg .u32 m;\n\tsub.cc.u32 %0, %2, %4;\n\tsubc.cc.u32 %1, %3, %5;\n\tsubc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\tsubc.cc.u32 %1, %1, 0;\n\tsubc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\tsubc.u32 %1, %1, 0;\n\t}"
+        : "=r"(s0), "=r"(s1) : "r"(a0), "r"(a1), "r"(t0), "r"(t1));
+    return pack64(s0, s1);
+}
+#else
+inline u64 add_lc(u64 a, u64 t) {
     u64 s = a + t;
     return s < a ? s + EPS : s;
 }
-GL_HD u64 sub_lc(u64 a, u64 t) {
+inline u64 sub_lc(u64 a, u64 t) {
     u64 d = a - t;
     return a < t ? d - EPS : d;
 }
-// ll: both operands arbitrary u64 -> up to two repairs.
-GL_HD u64 add_ll(u64 a, u64 b) {
+inline u64 add_ll(u64 a, u64 b) {
     u64 s = a + b;
     if (s < a) { u64 s2 = s + EPS; s = s2 < s ? s2 + EPS : s2; }
     return s;
 }
-GL_HD u64 sub_ll(u64 a, u64 b) {
+inline u64 sub_ll(u64 a, u64 b) {
     u64 d = a - b;
     if (a < b) { u64 d2 = d - EPS; d = d < EPS ? d2 - EPS : d2; }
     return d;
 }
+#endif
 
 // ---- Montgomery multiplication ---------------------------------------------------------
 // returns a*b*2^-64 mod p, canonical, provided a*b < p * 2^64 (i.e. one operand < p).
 GL_HD u64 mont_reduce(u64 hi, u64 lo) {
+#if defined(__CUDA_ARCH__)
+    // A1 = lo1 + lo0 (carry e); b = (A1:lo0) - (A1 + e)  [A1 + e never wraps]; r = hi - b (+p on borrow)
+    u32 r0, r1, r2, r3, q0, q1;
+    unpack64(lo, r0, r1); unpack64(hi, r2, r3);
+    asm("{\n\t.reg .u32 A1, e, B0, B1, m;\n\t"
+        "add.cc.u32 A1, %3, %2;\n\taddc.u32 e, 0, 0;\n\tadd.u32 e, e, A1;\n\t"
+        "sub.cc.u32 B0, %2, e;\n\tsubc.u32 B1, A1, 0;\n\t"
+        "sub.cc.u32 %0, %4, B0;\n\tsubc.cc.u32 %1, %5, B1;\n\tsubc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\tsubc.u32 %1, %1, 0;\n\t}"
+        : "=&r"(q0), "=&r"(q1) : "r"(r0), "r"(r1), "r"(r2), "r"(r3));
+    return pack64(q0, q1);
+#else
     u64 a = lo + (lo << 32);
     u64 e = a < lo;                    // carry out of the 64-bit add
     u64 b = a - (a >> 32) - e;         // never underflows: a >= (a>>32) + e
     u64 r = hi - b;
     return hi < b ? r - EPS : r;       // + p
+#endif
 }
 GL_HD u64 mul(u64 a, u64 b) {
 #if defined(__CUDA_ARCH__)

@@ -42,6 +42,7 @@ __device__ __forceinline__ u32 padi(u32 i) { return i + (i >> 4); }
 struct TileCtx {
     u64 in_base, out_base, low_base;
     const u64 *sc_lo, *sc_hi;
+    const u64 *pre_tab;
     u64 pre_step;
 };
 
@@ -72,11 +73,17 @@ __device__ __forceinline__ void do_step(u64 *sm, const PassParams &p, const Tabl
         if (FIRST && p.has_pre) {
             // x[k] *= q^(in index), in index = A + k * (in_rs << (f - log_w))
             u64 A = tc.in_base + (u64)rpos0 * p.in_rs + (u64)c * p.in_cs;
-            u64 t = tw_lookup(tc.sc_lo, tc.sc_hi, p.hi_len, A);
-            static_for<0, RAD>([&](auto K) {
-                x[K] = mul(x[K], t);
-                if constexpr (decltype(K)::value + 1 < RAD) t = mul(t, tc.pre_step);
-            });
+            if (tc.pre_tab) {
+                const u64 *pt = tc.pre_tab + A;
+                const u64 stj = p.in_rs << (f - p.log_w);
+                static_for<0, RAD>([&](auto K) { x[K] = mul(x[K], __ldg(pt + (u64)K * stj)); });
+            } else {
+                u64 t = tw_lookup(tc.sc_lo, tc.sc_hi, p.hi_len, A);
+                static_for<0, RAD>([&](auto K) {
+                    x[K] = mul(x[K], t);
+                    if constexpr (decltype(K)::value + 1 < RAD) t = mul(t, tc.pre_step);
+                });
+            }
         }
 
         dft_regs<B, INV>(x);
@@ -105,25 +112,43 @@ __device__ __forceinline__ void do_step(u64 *sm, const PassParams &p, const Tabl
             bool scaled = false;
             if (p.has_outer) {
                 const u64 lower = tc.low_base + (u64)c * p.low_cs;
-                const u64 A = ((u64)iR0 * lower * p.outer_mult) & p.n_mask;
-                const u64 Bs = ((lower << SH) * p.outer_mult) & p.n_mask;
-                u64 t = tw_lookup(tb.tw_lo, tb.tw_hi, p.hi_len, A);
-                const u64 st = tw_lookup(tb.tw_lo, tb.tw_hi, p.hi_len, Bs);
-                static_for<0, RAD>([&](auto KAP) {
-                    constexpr int q = brev_c(decltype(KAP)::value, B);
-                    x[q] = mul(x[q], t);
-                    if constexpr (decltype(KAP)::value + 1 < RAD) t = mul(t, st);
-                });
+                if (p.outer_tab) {
+                    const u64 *ot = p.outer_tab + (u64)iR0 * p.outer_S + lower;
+                    const u64 stj = p.outer_S << SH;
+                    static_for<0, RAD>([&](auto KAP) {
+                        constexpr int q = brev_c(decltype(KAP)::value, B);
+                        x[q] = mul(x[q], __ldg(ot + (u64)KAP * stj));
+                    });
+                } else {
+                    const u64 A = ((u64)iR0 * lower * p.outer_mult) & p.n_mask;
+                    const u64 Bs = ((lower << SH) * p.outer_mult) & p.n_mask;
+                    u64 t = tw_lookup(tb.tw_lo, tb.tw_hi, p.hi_len, A);
+                    const u64 st = tw_lookup(tb.tw_lo, tb.tw_hi, p.hi_len, Bs);
+                    static_for<0, RAD>([&](auto KAP) {
+                        constexpr int q = brev_c(decltype(KAP)::value, B);
+                        x[q] = mul(x[q], t);
+                        if constexpr (decltype(KAP)::value + 1 < RAD) t = mul(t, st);
+                    });
+                }
                 scaled = true;
             }
             if (p.has_post) {
                 const u64 A = tc.out_base + (u64)c * p.out_cs + (u64)iR0 * p.out_rs;
-                u64 t = tw_lookup(tc.sc_lo, tc.sc_hi, p.hi_len, A);
-                static_for<0, RAD>([&](auto KAP) {
-                    constexpr int q = brev_c(decltype(KAP)::value, B);
-                    x[q] = mul(x[q], t);
-                    if constexpr (decltype(KAP)::value + 1 < RAD) t = mul(t, p.post_step);
-                });
+                if (p.post_tab) {
+                    const u64 *pt = p.post_tab + A;
+                    const u64 stj = p.out_rs << SH;
+                    static_for<0, RAD>([&](auto KAP) {
+                        constexpr int q = brev_c(decltype(KAP)::value, B);
+                        x[q] = mul(x[q], __ldg(pt + (u64)KAP * stj));
+                    });
+                } else {
+                    u64 t = tw_lookup(tc.sc_lo, tc.sc_hi, p.hi_len, A);
+                    static_for<0, RAD>([&](auto KAP) {
+                        constexpr int q = brev_c(decltype(KAP)::value, B);
+                        x[q] = mul(x[q], t);
+                        if constexpr (decltype(KAP)::value + 1 < RAD) t = mul(t, p.post_step);
+                    });
+                }
                 scaled = true;
             }
             if (!scaled) {
@@ -158,7 +183,9 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(const PassParams p, const
     const u32 nthreads = blockDim.x, tid = threadIdx.x;
 
     // ---- batch decode
-    const u32 b = blockIdx.y;
+    // linear block id = tile * nbatch + batch: the batch (column / coset / lane) varies fastest, so the
+    // CTAs that share a twiddle-table tile run together and the tables are served from L2
+    const u32 b = blockIdx.x % p.nbatch;
     const u32 lane = b % p.lanes;
     const u32 cos = (b / p.lanes) % p.ncos;
     const u32 col = b / (p.lanes * p.ncos);
@@ -169,7 +196,7 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(const PassParams p, const
     TileCtx tc;
     tc.in_base = tc.out_base = tc.low_base = 0;
     {
-        u32 t = blockIdx.x;
+        u32 t = blockIdx.x / p.nbatch;
         for (u32 d = 0; d < p.ndims; d++) {
             u32 idx = t % p.dims[d].ext;
             t /= p.dims[d].ext;
@@ -181,6 +208,7 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(const PassParams p, const
     tc.sc_lo = tb.sc_lo ? tb.sc_lo + (u64)cos * 4096 : nullptr;
     tc.sc_hi = tb.sc_hi ? tb.sc_hi + (u64)cos * p.hi_len : nullptr;
     tc.pre_step = (p.has_pre && tb.pre_step) ? tb.pre_step[cos] : 0;
+    tc.pre_tab = p.pre_tab ? p.pre_tab + (u64)cos * p.pre_cos_stride : nullptr;
 
     // ---- global -> shared (coalesced along whichever tile dimension is contiguous)
     const u32 es = p.estride;
@@ -238,7 +266,7 @@ static void launch_t(const PassParams &p, const Tables &t, bool inverse, const u
     const unsigned T = 1u << (LOGR + p.log_w);
     const unsigned threads = T / kElemsPerThread;
     const size_t smem = (size_t)(T + (T >> 4) + 1) * sizeof(u64);
-    dim3 grid(ntiles, nbatch);
+    dim3 grid(ntiles * nbatch);
     if (inverse)
         ntt_pass_kernel<LOGR, true><<<grid, threads, smem, stream>>>(p, t, in, out);
     else
@@ -254,6 +282,27 @@ void launch_pass(const PassParams &p, const Tables &t, bool inverse, const u64 *
 #undef MS_CASE
         default: break;
     }
+}
+
+__global__ void build_pow_table_kernel(u64 *dst, u64 count, const u64 *lo, const u64 *hi, u32 hi_len) {
+    const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (i < count) dst[i] = tw_lookup(lo, hi, hi_len, i);
+}
+__global__ void build_outer_table_kernel(u64 *dst, u64 count, u64 S, u64 mult, u64 n_mask, const u64 *lo, const u64 *hi,
+                                         u32 hi_len) {
+    const u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const u64 iR = i / S, lower = i % S;
+    dst[i] = tw_lookup(lo, hi, hi_len, (iR * lower * mult) & n_mask);
+}
+void build_pow_table(u64 *dst, u64 count, const u64 *lo, const u64 *hi, u32 hi_len, cudaStream_t stream) {
+    build_pow_table_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(dst, count, lo, hi, hi_len);
+}
+void build_outer_table(u64 *dst, u64 R, u64 S, u64 mult, u64 n_mask, const u64 *lo, const u64 *hi, u32 hi_len,
+                       cudaStream_t stream) {
+    const u64 count = R * S;
+    build_outer_table_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(dst, count, S, mult, n_mask, lo, hi,
+                                                                                    hi_len);
 }
 
 void steps_of(int log_r, int out[3], int *nsteps) {

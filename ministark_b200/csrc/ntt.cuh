@@ -46,6 +46,14 @@ struct PassParams {
     u64 in_col_stride, out_col_stride;   // words
     u64 in_cos_stride, out_cos_stride;   // words
     u32 estride;                         // words per element (1 Fp, 3 Fq3)
+    u32 nbatch;                          // columns * coset blocks * lanes (linear block id % nbatch)
+    // optional full tables (replace the per-thread geometric progressions: one multiplication per
+    // element instead of two; shared by every column / coset of the batch, so they stay in L2)
+    const u64 *outer_tab;                // [i_R * outer_S + lower] = omega_{N_k}^(i_R * lower)
+    u64 outer_S;
+    const u64 *pre_tab;                  // [cos * pre_cos_stride + j] = q_cos^j
+    u64 pre_cos_stride;
+    const u64 *post_tab;                 // [i] = c * q^i
 };
 
 struct Tables {
@@ -71,5 +79,9 @@ void launch_naive(const u64 *in, u64 in_stride_words, u64 *out, u64 out_stride_w
                   unsigned lanes, unsigned ncols, bool inverse, u64 root_mont, u64 offset_mont, cudaStream_t stream);
 
 void upload_constants();
+// table builders (device kernels): dst[i] = lookup2(lo, hi, hi_len, i) and the outer-twiddle table
+void build_pow_table(u64 *dst, u64 count, const u64 *lo, const u64 *hi, u32 hi_len, cudaStream_t stream);
+void build_outer_table(u64 *dst, u64 R, u64 S, u64 mult, u64 n_mask, const u64 *lo, const u64 *hi, u32 hi_len,
+                       cudaStream_t stream);
 
 }  // namespace msntt
