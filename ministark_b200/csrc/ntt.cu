@@ -43,8 +43,16 @@ struct TileCtx {
     u64 in_base, out_base, low_base;
     const u64 *sc_lo, *sc_hi;
     const u64 *pre_tab;
+    const u64 *sm2;   // last-step multiplier tile prefetched into shared memory (or nullptr)
     u64 pre_step;
 };
+
+__device__ __forceinline__ void cp_async8(u64 *smem_dst, const u64 *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ u64 tw_lookup(const u64 *lo, const u64 *hi, u32 hi_len, u64 e) {
     u64 t = lo[e & 4095];
@@ -70,20 +78,15 @@ __device__ __forceinline__ void do_step(u64 *sm, const PassParams &p, const Tabl
         u64 x[RAD];
         static_for<0, RAD>([&](auto K) { x[K] = sm[padi(i0 + ((u32)K << f))]; });
 
-        if (FIRST && p.has_pre) {
+        if (FIRST && p.has_pre && !tc.pre_tab) {
+            // (with a full pre-scale table the factor was applied while loading the tile)
             // x[k] *= q^(in index), in index = A + k * (in_rs << (f - log_w))
             u64 A = tc.in_base + (u64)rpos0 * p.in_rs + (u64)c * p.in_cs;
-            if (tc.pre_tab) {
-                const u64 *pt = tc.pre_tab + A;
-                const u64 stj = p.in_rs << (f - p.log_w);
-                static_for<0, RAD>([&](auto K) { x[K] = mul(x[K], __ldg(pt + (u64)K * stj)); });
-            } else {
-                u64 t = tw_lookup(tc.sc_lo, tc.sc_hi, p.hi_len, A);
-                static_for<0, RAD>([&](auto K) {
-                    x[K] = mul(x[K], t);
-                    if constexpr (decltype(K)::value + 1 < RAD) t = mul(t, tc.pre_step);
-                });
-            }
+            u64 t = tw_lookup(tc.sc_lo, tc.sc_hi, p.hi_len, A);
+            static_for<0, RAD>([&](auto K) {
+                x[K] = mul(x[K], t);
+                if constexpr (decltype(K)::value + 1 < RAD) t = mul(t, tc.pre_step);
+            });
         }
 
         dft_regs<B, INV>(x);
@@ -110,45 +113,34 @@ __device__ __forceinline__ void do_step(u64 *sm, const PassParams &p, const Tabl
             }
             constexpr int SH = B1 + B2;  // kappa of this field enters i_R shifted by SH
             bool scaled = false;
-            if (p.has_outer) {
-                const u64 lower = tc.low_base + (u64)c * p.low_cs;
-                if (p.outer_tab) {
-                    const u64 *ot = p.outer_tab + (u64)iR0 * p.outer_S + lower;
-                    const u64 stj = p.outer_S << SH;
-                    static_for<0, RAD>([&](auto KAP) {
-                        constexpr int q = brev_c(decltype(KAP)::value, B);
-                        x[q] = mul(x[q], __ldg(ot + (u64)KAP * stj));
-                    });
-                } else {
-                    const u64 A = ((u64)iR0 * lower * p.outer_mult) & p.n_mask;
-                    const u64 Bs = ((lower << SH) * p.outer_mult) & p.n_mask;
-                    u64 t = tw_lookup(tb.tw_lo, tb.tw_hi, p.hi_len, A);
-                    const u64 st = tw_lookup(tb.tw_lo, tb.tw_hi, p.hi_len, Bs);
-                    static_for<0, RAD>([&](auto KAP) {
-                        constexpr int q = brev_c(decltype(KAP)::value, B);
-                        x[q] = mul(x[q], t);
-                        if constexpr (decltype(KAP)::value + 1 < RAD) t = mul(t, st);
-                    });
-                }
+            if (tc.sm2) {
+                // inter-pass twiddle / inverse post-scale from the prefetched tile: row = output index
+                static_for<0, RAD>([&](auto KAP) {
+                    constexpr int q = brev_c(decltype(KAP)::value, B);
+                    const u32 row = iR0 + ((u32)KAP << SH);
+                    x[q] = mul(x[q], tc.sm2[padi((row << p.log_w) + c)]);
+                });
                 scaled = true;
-            }
-            if (p.has_post) {
+            } else if (p.has_outer) {
+                const u64 lower = tc.low_base + (u64)c * p.low_cs;
+                const u64 A = ((u64)iR0 * lower * p.outer_mult) & p.n_mask;
+                const u64 Bs = ((lower << SH) * p.outer_mult) & p.n_mask;
+                u64 t = tw_lookup(tb.tw_lo, tb.tw_hi, p.hi_len, A);
+                const u64 st = tw_lookup(tb.tw_lo, tb.tw_hi, p.hi_len, Bs);
+                static_for<0, RAD>([&](auto KAP) {
+                    constexpr int q = brev_c(decltype(KAP)::value, B);
+                    x[q] = mul(x[q], t);
+                    if constexpr (decltype(KAP)::value + 1 < RAD) t = mul(t, st);
+                });
+                scaled = true;
+            } else if (p.has_post) {
                 const u64 A = tc.out_base + (u64)c * p.out_cs + (u64)iR0 * p.out_rs;
-                if (p.post_tab) {
-                    const u64 *pt = p.post_tab + A;
-                    const u64 stj = p.out_rs << SH;
-                    static_for<0, RAD>([&](auto KAP) {
-                        constexpr int q = brev_c(decltype(KAP)::value, B);
-                        x[q] = mul(x[q], __ldg(pt + (u64)KAP * stj));
-                    });
-                } else {
-                    u64 t = tw_lookup(tc.sc_lo, tc.sc_hi, p.hi_len, A);
-                    static_for<0, RAD>([&](auto KAP) {
-                        constexpr int q = brev_c(decltype(KAP)::value, B);
-                        x[q] = mul(x[q], t);
-                        if constexpr (decltype(KAP)::value + 1 < RAD) t = mul(t, p.post_step);
-                    });
-                }
+                u64 t = tw_lookup(tc.sc_lo, tc.sc_hi, p.hi_len, A);
+                static_for<0, RAD>([&](auto KAP) {
+                    constexpr int q = brev_c(decltype(KAP)::value, B);
+                    x[q] = mul(x[q], t);
+                    if constexpr (decltype(KAP)::value + 1 < RAD) t = mul(t, p.post_step);
+                });
                 scaled = true;
             }
             if (!scaled) {
@@ -210,31 +202,73 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(const PassParams p, const
     tc.pre_step = (p.has_pre && tb.pre_step) ? tb.pre_step[cos] : 0;
     tc.pre_tab = p.pre_tab ? p.pre_tab + (u64)cos * p.pre_cos_stride : nullptr;
 
-    // ---- global -> shared (coalesced along whichever tile dimension is contiguous)
+    // ---- prefetch the last step's multiplier tile (inter-pass twiddles, or the inverse post-scale) into
+    //      the second shared buffer with cp.async: it lands while the sub-NTT runs
+    const int lw = p.log_w;
+    tc.sm2 = nullptr;
+    {
+        const u64 *ltab = nullptr;
+        u64 lrs = 0, lcs = 0;
+        if (p.has_outer && p.outer_tab) {
+            ltab = p.outer_tab + tc.low_base; lrs = p.outer_S; lcs = p.low_cs;
+        } else if (p.has_post && p.post_tab) {
+            ltab = p.post_tab + tc.out_base; lrs = p.out_rs; lcs = p.out_cs;
+        }
+        if (ltab) {
+            u64 *sm2 = sm + (T + (T >> 4) + 1);
+            tc.sm2 = sm2;
+#pragma unroll
+            for (int k = 0; k < kElemsPerThread; k++) {
+                const u32 i = k * nthreads + tid;
+                const u32 c = i & (W - 1), r = i >> lw;
+                cp_async8(sm2 + padi(i), ltab + (u64)r * lrs + (u64)c * lcs);
+            }
+            cp_async_commit();
+        }
+    }
+
+    // ---- global -> shared (coalesced along whichever tile dimension is contiguous); T = 16 * nthreads.
+    //      With a full pre-scale table the coset factor offset^j is applied right here.
     const u32 es = p.estride;
-    if (p.in_r_fast) {
-        for (u32 i = tid; i < T; i += nthreads) {
-            u32 r = i & (R - 1), c = i >> LOGR;
-            sm[padi((r << p.log_w) + c)] = src[(tc.in_base + (u64)r * p.in_rs + (u64)c * p.in_cs) * es];
+    {
+        u64 v[kElemsPerThread];
+        u32 sidx[kElemsPerThread];
+        const bool pre = p.has_pre && tc.pre_tab;
+        u64 tw[kElemsPerThread];
+#pragma unroll
+        for (int k = 0; k < kElemsPerThread; k++) {
+            const u32 i = k * nthreads + tid;
+            u32 r, c;
+            if (p.in_r_fast) { r = i & (R - 1); c = i >> LOGR; } else { c = i & (W - 1); r = i >> lw; }
+            const u64 e = tc.in_base + (u64)r * p.in_rs + (u64)c * p.in_cs;
+            sidx[k] = padi((r << lw) + c);
+            v[k] = src[e * es];
+            if (pre) tw[k] = __ldg(tc.pre_tab + e);
         }
-    } else {
-        for (u32 i = tid; i < T; i += nthreads) {
-            u32 c = i & (W - 1), r = i >> p.log_w;
-            sm[padi(i)] = src[(tc.in_base + (u64)r * p.in_rs + (u64)c * p.in_cs) * es];
-        }
+#pragma unroll
+        for (int k = 0; k < kElemsPerThread; k++) sm[sidx[k]] = pre ? mul(v[k], tw[k]) : v[k];
     }
     __syncthreads();
 
-    // ---- CTA-level sub-NTT
-    const int lw = p.log_w;
+    // ---- CTA-level sub-NTT (the prefetched multiplier tile must be complete and visible to all
+    //      threads before the last step)
+    auto tile_ready = [&]() {
+        if (tc.sm2) {
+            cp_async_wait_all();
+            __syncthreads();
+        }
+    };
     if constexpr (S::N == 1) {
+        tile_ready();
         do_step<S::A, INV, true, true, 0, 0, LOGR>(sm, p, tb, tc, lw, 0);
     } else if constexpr (S::N == 2) {
         do_step<S::A, INV, true, false, 0, 0, LOGR>(sm, p, tb, tc, lw + LOGR - S::A, LOGR - S::A);
+        tile_ready();
         do_step<S::Bb, INV, false, true, S::A, 0, LOGR>(sm, p, tb, tc, lw, 0);
     } else {
         do_step<S::A, INV, true, false, 0, 0, LOGR>(sm, p, tb, tc, lw + LOGR - S::A, LOGR - S::A);
         do_step<S::Bb, INV, false, false, S::A, 0, LOGR>(sm, p, tb, tc, lw + S::C, S::C);
+        tile_ready();
         do_step<S::C, INV, false, true, S::A, S::Bb, LOGR>(sm, p, tb, tc, lw, 0);
     }
 
@@ -247,16 +281,12 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(const PassParams p, const
         u32 k1 = rho & ((1u << S::A) - 1), k2 = (rho >> S::A) & ((1u << S::Bb) - 1), k3 = rho >> (S::A + S::Bb);
         return (k1 << (LOGR - S::A)) | (k2 << S::C) | k3;
     };
-    if (p.out_r_fast) {
-        for (u32 i = tid; i < T; i += nthreads) {
-            u32 rho = i & (R - 1), c = i >> LOGR;
-            dst[(tc.out_base + (u64)rho * p.out_rs + (u64)c * p.out_cs) * es] = sm[padi((pos_of(rho) << p.log_w) + c)];
-        }
-    } else {
-        for (u32 i = tid; i < T; i += nthreads) {
-            u32 c = i & (W - 1), rho = i >> p.log_w;
-            dst[(tc.out_base + (u64)rho * p.out_rs + (u64)c * p.out_cs) * es] = sm[padi((pos_of(rho) << p.log_w) + c)];
-        }
+#pragma unroll
+    for (int k = 0; k < kElemsPerThread; k++) {
+        const u32 i = k * nthreads + tid;
+        u32 rho, c;
+        if (p.out_r_fast) { rho = i & (R - 1); c = i >> LOGR; } else { c = i & (W - 1); rho = i >> lw; }
+        dst[(tc.out_base + (u64)rho * p.out_rs + (u64)c * p.out_cs) * es] = sm[padi((pos_of(rho) << lw) + c)];
     }
 }
 
@@ -265,7 +295,14 @@ static void launch_t(const PassParams &p, const Tables &t, bool inverse, const u
                      unsigned nbatch, cudaStream_t stream) {
     const unsigned T = 1u << (LOGR + p.log_w);
     const unsigned threads = T / kElemsPerThread;
-    const size_t smem = (size_t)(T + (T >> 4) + 1) * sizeof(u64);
+    const bool two = (p.has_outer && p.outer_tab) || (p.has_post && p.post_tab);
+    const size_t smem = (size_t)(T + (T >> 4) + 1) * sizeof(u64) * (two ? 2 : 1);
+    static bool attr_set = false;   // per instantiation: allow > 48 KiB of dynamic shared memory
+    if (!attr_set) {
+        cudaFuncSetAttribute(ntt_pass_kernel<LOGR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+        cudaFuncSetAttribute(ntt_pass_kernel<LOGR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+        attr_set = true;
+    }
     dim3 grid(ntiles * nbatch);
     if (inverse)
         ntt_pass_kernel<LOGR, true><<<grid, threads, smem, stream>>>(p, t, in, out);

@@ -1,0 +1,110 @@
+"""CPU, world_size 2 over gloo: the multi-GPU host logic of ministark_b200/parallel.py (column
+blocks -> all-to-all row slabs -> subtree roots -> all-gather -> merged root) with the CPU oracle
+plugged in as the compute engine.  The merged root must equal the single-process root of the
+full matrix — the sharded commitment is bit-identical to the reference's single tree."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleEngine:
+    """CPU stand-in for CudaEngine: torch CPU tensors + oracle/gl_oracle.c"""
+
+    def __init__(self):
+        import torch
+        from oracle import oracle
+        self.torch, self.orc = torch, oracle
+
+    def empty(self, shape):
+        return self.torch.zeros(shape, dtype=self.torch.int64)
+
+    def view(self, buf, col, lo, hi):
+        return buf[col, lo:hi]
+
+    def _np(self, t):
+        return t.numpy().view(np.uint64)
+
+    def intt(self, src, dst, log_n, ncols):
+        dst.copy_(self.torch.from_numpy(self.orc.ntt(self._np(src), 1, log_n, inverse=True).view(np.int64)))
+
+    def lde(self, coeffs, out, log_n, log_b, ncols):
+        out.copy_(self.torch.from_numpy(self.orc.lde(self._np(coeffs), 1, log_n, log_b, self.orc.generator(), True).view(np.int64)))
+
+    def subtree_root(self, slab, nrows, ncols):
+        leaves = self.orc.hash_rows(np.ascontiguousarray(self._np(slab)), 1)
+        if nrows == 1:
+            return leaves[0].tobytes()
+        return self.orc.merkle_nodes(leaves)[1].tobytes()
+
+    def gather_digests(self, dist, digest, world):
+        t = self.torch.frombuffer(bytearray(digest), dtype=self.torch.uint8)
+        out = [self.torch.empty(32, dtype=self.torch.uint8) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [o.numpy().tobytes() for o in out]
+
+
+def _worker(rank, world, port, log_n, log_b, ncols, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from ministark_b200 import parallel
+    from oracle import oracle as orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = orc.rand_matrix(ncols, 1 << log_n, 1, seed=77)          # every rank can regenerate the trace
+        eng = OracleEngine()
+        sc = parallel.ShardedCommit(eng, dist, log_n, log_b, ncols)
+        lo, hi = sc.lo, sc.hi
+        import torch
+        sc.transform(torch.from_numpy(full[lo:hi].view(np.int64).copy()))
+        root = sc.commit()
+        q.put((rank, root))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("log_n,log_b,ncols", [(6, 3, 8), (5, 1, 2)])
+def test_sharded_commit_world2_matches_single_tree(orc, log_n, log_b, ncols):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, log_n, log_b, ncols, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    roots = dict(q.get(timeout=60) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = orc.rand_matrix(ncols, 1 << log_n, 1, seed=77)
+    lde = orc.lde(orc.ntt(full, 1, log_n, inverse=True), 1, log_n, log_b, orc.generator(), True)
+    want = orc.merkle_nodes(orc.hash_rows(lde, 1))[1].tobytes()
+    assert roots[0] == roots[1] == want
+
+
+def test_merge_subtree_roots_and_blocks(orc):
+    from ministark_b200 import parallel
+    leaves = orc.hash_rows(orc.rand_matrix(3, 16, 1, seed=1), 1)
+    nodes = orc.merkle_nodes(leaves)
+    # subtree roots of 4 slabs of 4 leaves are the level-2 nodes 4..7 of the heap layout
+    subs = [orc.merkle_nodes(leaves[4 * d:4 * d + 4])[1].tobytes() for d in range(4)]
+    assert subs == [nodes[4 + d].tobytes() for d in range(4)]
+    assert parallel.merge_subtree_roots(subs) == nodes[1].tobytes()
+    assert parallel.merge_subtree_roots(subs[:1]) == subs[0]
+    assert [parallel.column_block(32, 4, r) for r in range(4)] == [(0, 8), (8, 16), (16, 24), (24, 32)]
+    with pytest.raises(AssertionError):
+        parallel.merge_subtree_roots(subs[:3])
