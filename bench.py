@@ -170,7 +170,10 @@ def workload_config(args):
                         "(bit-reversed) + SHA-256 Merkle commit + constraint eval (32 degree-2 transition constraints, ce_blowup 1)",
             "log_n": args.log_n, "ncols": args.ncols, "blowup": 1 << LOG_BLOWUP,
             "l2_policy": "inputs (>= 4 GiB per phase) far exceed the 126 MB L2; no explicit flush",
-            "parallelism": f"{args.gpus} x independent trace shard (columns/job per GPU), no data-path collective"}
+            "parallelism": ("single GPU" if args.gpus == 1 else
+                            f"{args.gpus} ranks: one {args.ncols * args.gpus}-column trace, {args.ncols}-column block per rank "
+                            "(iNTT/LDE local), all-to-all into row slabs for the leaf hash, all-gather of subtree roots "
+                            "and of the partial composition sums")}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -196,30 +199,43 @@ def run_gpu(args):
     ctx = ms.Context(local, stream=stream.cuda_stream)
 
     dev = torch.device("cuda", local)
-    trace = torch.empty((ncols, n), dtype=torch.int64, device=dev)
-    polys = torch.empty((ncols, n), dtype=torch.int64, device=dev)
-    lde = torch.empty((ncols, N), dtype=torch.int64, device=dev)
-    leaves = torch.empty((N, 4), dtype=torch.int64, device=dev)
-    nodes = torch.empty((N, 4), dtype=torch.int64, device=dev)
-    ce_out = torch.empty(n, dtype=torch.int64, device=dev)
-    ctx.fill_random(trace, ncols * n, 3000 + rank)
+    from ministark_b200.pipeline import TraceCommitPipeline
     evaluator = synth_air.GpuConstraintEval(ctx, log_n, log_b, ncols, dev)
+    pipe = TraceCommitPipeline(ctx, dev, log_n, log_b, ncols, evaluator=evaluator, chunk_cols=4, stream=stream)
+    trace, polys, lde, ce_out = pipe.trace, pipe.polys, pipe.lde, pipe.ce
+    ctx.fill_random(trace, ncols * n, 3000 + rank)
     host_trace = None
+    sharded = partials = None
+    if world > 1:
+        # one trace of ncols*world columns, column blocks sharded over the ranks (ministark_b200/parallel.py):
+        # local iNTT + LDE, all-to-all into row slabs, slab hash + subtree, all-gather of the subtree roots;
+        # the composition is a sum over column-local constraint groups: partial sums are all-gathered and added
+        from ministark_b200 import parallel
+        sharded = parallel.ShardedCommit(parallel.CudaEngine(ctx, dev), dist, log_n, log_b, ncols * world,
+                                         polys=polys, lde=lde)
+        partials = torch.empty((world, n), dtype=torch.int64, device=dev)
 
-    def step(from_host=False):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    def commit():
+        return sharded.commit() if sharded is not None else pipe.commit()
+
+    def evaluate():
+        pipe.evaluate()
+        if sharded is not None:
+            dist.all_gather_into_tensor(partials, ce_out)
+            ctx.sum_columns(partials, ce_out, ms.FP, n, world)
+
+    def step():
+        """device-resident step, phase by phase (the same calls TraceCommitPipeline.run_resident makes)"""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         ev[0].record()
-        if from_host:
-            trace.copy_(host_trace, non_blocking=True)
-        ev[1].record()
         ctx.ntt_batch_to(trace, polys, ms.FP, log_n, ncols, inverse=True)
-        ev[2].record()
+        ev[1].record()
         ctx.lde_batch(polys, lde, ms.FP, log_n, log_b, ncols, offset=ms.GENERATOR, bitrev=True)
+        ev[2].record()
+        root = commit()                                                                # D2H of the 32-byte root
         ev[3].record()
-        root = ctx.merkle_commit(lde, ms.FP, N, ncols, leaves=leaves, nodes=nodes)   # D2H of the 32-byte root
+        evaluate()
         ev[4].record()
-        evaluator.run(lde, ce_out)
-        ev[5].record()
         return ev, root
 
     def barrier():
@@ -247,7 +263,7 @@ def run_gpu(args):
     launches = ctx.launches - l0
     clk = clocks.stop()
     total_ms = t_start.elapsed_time(t_end)
-    names = ["h2d", "intt", "lde", "merkle", "constraint_eval"]
+    names = ["intt", "lde", "merkle", "constraint_eval"]
     phase_ms = {nm: sum(e[i].elapsed_time(e[i + 1]) for e in evs) / args.steps for i, nm in enumerate(names)}
     if world > 1:
         t = torch.tensor([total_ms], device=dev)
@@ -257,20 +273,31 @@ def run_gpu(args):
     ops = field_ops(log_n, log_b, ncols) * world
     value = ops / (ms_per_step / 1000)
 
-    # ---- end to end through the public API with HOST buffers: pinned host trace -> H2D -> pipeline
-    #      -> D2H of the Merkle root and of the constraint-evaluation column
+    # ---- end to end through the public API (TraceCommitPipeline.run_from_host) with HOST buffers: pinned
+    #      host trace -> chunked H2D overlapped with iNTT/LDE -> Merkle commit -> constraint evaluation
+    #      -> D2H of the root and of the composition-evaluation column
     host_trace = torch.empty((ncols, n), dtype=torch.int64, pin_memory=True)
     host_trace.copy_(trace)
-    host_ce = torch.empty(n, dtype=torch.int64, pin_memory=True)
     e2e_steps = max(1, min(args.steps, 3))
-    step(True)
+    host_ce = torch.empty(n, dtype=torch.int64, pin_memory=True)
+
+    def e2e_step():
+        if sharded is None:
+            return pipe.run_from_host(host_trace)[0]
+        trace.copy_(host_trace, non_blocking=True)
+        _, r = step()
+        host_ce.copy_(ce_out, non_blocking=True)
+        return r
+
+    e2e_step()
     barrier()
     t_start.record()
+    e2e_root = None
     for _ in range(e2e_steps):
-        step(True)
-        host_ce.copy_(ce_out, non_blocking=True)
+        e2e_root = e2e_step()
     t_end.record()
     barrier()
+    assert e2e_root == root, "e2e path and resident path disagree on the Merkle root"
     e2e_ms = t_start.elapsed_time(t_end) / e2e_steps
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev)

@@ -167,7 +167,7 @@ struct Steps {
 };
 
 template <int LOGR, bool INV>
-__global__ void __launch_bounds__(256) ntt_pass_kernel(const PassParams p, const Tables tb, const u64 *__restrict__ in,
+__global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, const Tables tb, const u64 *__restrict__ in,
                                                        u64 *__restrict__ out) {
     extern __shared__ u64 sm[];
     using S = Steps<LOGR>;
@@ -231,22 +231,28 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(const PassParams p, const
     //      With a full pre-scale table the coset factor offset^j is applied right here.
     const u32 es = p.estride;
     {
-        u64 v[kElemsPerThread];
-        u32 sidx[kElemsPerThread];
         const bool pre = p.has_pre && tc.pre_tab;
-        u64 tw[kElemsPerThread];
+        constexpr int CH = 8;   // loads in flight per thread and batch
+#pragma unroll 1
+        for (int k0 = 0; k0 < kElemsPerThread; k0 += CH) {
+            u64 v[CH], tw[CH];
 #pragma unroll
-        for (int k = 0; k < kElemsPerThread; k++) {
-            const u32 i = k * nthreads + tid;
-            u32 r, c;
-            if (p.in_r_fast) { r = i & (R - 1); c = i >> LOGR; } else { c = i & (W - 1); r = i >> lw; }
-            const u64 e = tc.in_base + (u64)r * p.in_rs + (u64)c * p.in_cs;
-            sidx[k] = padi((r << lw) + c);
-            v[k] = src[e * es];
-            if (pre) tw[k] = __ldg(tc.pre_tab + e);
+            for (int k = 0; k < CH; k++) {
+                const u32 i = (k0 + k) * nthreads + tid;
+                u32 r, c;
+                if (p.in_r_fast) { r = i & (R - 1); c = i >> LOGR; } else { c = i & (W - 1); r = i >> lw; }
+                const u64 e = tc.in_base + (u64)r * p.in_rs + (u64)c * p.in_cs;
+                v[k] = src[e * es];
+                if (pre) tw[k] = __ldg(tc.pre_tab + e);
+            }
+#pragma unroll
+            for (int k = 0; k < CH; k++) {
+                const u32 i = (k0 + k) * nthreads + tid;
+                u32 r, c;
+                if (p.in_r_fast) { r = i & (R - 1); c = i >> LOGR; } else { c = i & (W - 1); r = i >> lw; }
+                sm[padi((r << lw) + c)] = pre ? mul(v[k], tw[k]) : v[k];
+            }
         }
-#pragma unroll
-        for (int k = 0; k < kElemsPerThread; k++) sm[sidx[k]] = pre ? mul(v[k], tw[k]) : v[k];
     }
     __syncthreads();
 
@@ -281,7 +287,7 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(const PassParams p, const
         u32 k1 = rho & ((1u << S::A) - 1), k2 = (rho >> S::A) & ((1u << S::Bb) - 1), k3 = rho >> (S::A + S::Bb);
         return (k1 << (LOGR - S::A)) | (k2 << S::C) | k3;
     };
-#pragma unroll
+#pragma unroll 4
     for (int k = 0; k < kElemsPerThread; k++) {
         const u32 i = k * nthreads + tid;
         u32 rho, c;

@@ -56,7 +56,7 @@ class ShardedCommit:
                                                            for nrows == 1 the single leaf digest
     """
 
-    def __init__(self, engine, dist, log_n, log_blowup, ncols_total):
+    def __init__(self, engine, dist, log_n, log_blowup, ncols_total, polys=None, lde=None):
         self.e, self.dist = engine, dist
         self.world = dist.get_world_size() if dist is not None else 1
         self.rank = dist.get_rank() if dist is not None else 0
@@ -70,8 +70,8 @@ class ShardedCommit:
             raise ValueError("rows and columns must divide evenly over the ranks")
         self.rows_per = self.N // self.world
         n = 1 << log_n
-        self.polys = engine.empty((self.nloc, n))
-        self.lde = engine.empty((self.nloc, self.N))
+        self.polys = polys if polys is not None else engine.empty((self.nloc, n))
+        self.lde = lde if lde is not None else engine.empty((self.nloc, self.N))
         self.slab = engine.empty((ncols_total, self.rows_per)) if self.world > 1 else None
 
     def transform(self, trace):
