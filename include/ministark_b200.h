@@ -143,11 +143,28 @@ int ms_fri_fold(ms_ctx *ctx, int field, const void *evals, unsigned log_n, unsig
  * words.  base_cols: nbase Fp columns, ext_cols: next columns of `fq_field` elements, each holding the
  * M = 2^log_m evaluations over the ce coset offset*<g_M> — in natural order, or (trace_bitrev != 0) as
  * the first M entries of a bit-reversed LDE column (what src/prover.rs:86-91 un-permutes on the CPU).
- * out: M elements of fq_field, natural order (one Fq value per ce-domain point). */
+ * out: M elements of fq_field (one Fq value per domain point), natural order, or — out_bitrev != 0 together
+ * with trace_bitrev — in the same bit-reversed order as the inputs (used by the DEEP composition, whose
+ * result feeds FRI in bit-reversed order, src/prover.rs:146-148). */
 int ms_eval_constraints(ms_ctx *ctx, const uint32_t *program, unsigned nprog, const uint64_t *consts,
                         unsigned nconsts, const void *base_cols, size_t base_stride_elems, unsigned nbase,
                         const void *ext_cols, size_t ext_stride_elems, unsigned next, int fq_field,
-                        unsigned log_m, uint64_t offset_mont, int trace_bitrev, void *out);
+                        unsigned log_m, uint64_t offset_mont, int trace_bitrev, int out_bitrev, void *out);
+
+/* same evaluator over an explicit table of DEVICE column pointers (columns from different matrices);
+ * col_is_fq[i] = 0: base-field column, 1: column of `fq_field` elements; out must be a device pointer */
+int ms_eval_constraints_ptrs(ms_ctx *ctx, const uint32_t *program, unsigned nprog, const uint64_t *consts,
+                             unsigned nconsts, const void *const *col_ptrs, const int *col_is_fq, unsigned ncols,
+                             int fq_field, unsigned log_m, uint64_t offset_mont, int trace_bitrev, int out_bitrev,
+                             void *out);
+
+/* ---- DEEP: out-of-domain evaluations, DeepPolyComposer::get_ood_evals (src/composer.rs:43-86) =
+ *      horner_evaluate (src/utils.rs:124-131) of every column at every point, as a parallel reduction ----
+ * coeffs: ncols columns of n coefficients of `field`; points: npoints Fq3 elements (3 words each);
+ * out[(col * npoints + k) * 3 ..] = P_col(points[k]) as Fq3.  The DEEP quotients themselves are evaluated
+ * pointwise over the LDE by ms_eval_constraints (program built by ministark_b200/deep.py). */
+int ms_poly_eval(ms_ctx *ctx, int field, const void *coeffs, size_t col_stride_elems, unsigned ncols, size_t n,
+                 const uint64_t *points, unsigned npoints, uint64_t *out);
 
 /* ---- synthetic data: splitmix64, reject >= p, store x*2^64 mod p ---- */
 int ms_fill_random(ms_ctx *ctx, void *dst, size_t nwords, uint64_t seed);

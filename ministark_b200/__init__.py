@@ -168,14 +168,33 @@ class Context:
 
     # ---- constraint evaluation
     def eval_constraints(self, program, out, log_m, base_cols=None, nbase=0, base_stride=None, ext_cols=None, next_=0,
-                         ext_stride=None, fq_field=FP, offset=GENERATOR, trace_bitrev=False):
+                         ext_stride=None, fq_field=FP, offset=GENERATOR, trace_bitrev=False, out_bitrev=False):
         """AirConfig::eval_constraint (src/air.rs:86-128): `program` from expr.compile_program."""
         m = 1 << log_m
         self._ck(self.lib.ms_eval_constraints(
             self.h, program.code.ctypes.data, len(program), program.consts.ctypes.data, program.consts.shape[0],
             _ptr(base_cols), m if base_stride is None else base_stride, nbase,
             _ptr(ext_cols), m if ext_stride is None else ext_stride, next_, fq_field, log_m, offset,
-            int(trace_bitrev), _ptr(out)))
+            int(trace_bitrev), int(out_bitrev), _ptr(out)))
+
+    def eval_constraints_ptrs(self, program, out, log_m, cols, cols_are_fq, fq_field=FP, offset=GENERATOR,
+                              trace_bitrev=False, out_bitrev=False):
+        """same evaluator over a list of resident columns (device buffers) that may live in different matrices"""
+        k = len(cols)
+        ptrs = (C.c_void_p * max(k, 1))(*[_ptr(c) for c in cols])
+        isq = (C.c_int * max(k, 1))(*[int(bool(q)) for q in cols_are_fq])
+        self._ck(self.lib.ms_eval_constraints_ptrs(self.h, program.code.ctypes.data, len(program),
+                                                   program.consts.ctypes.data, program.consts.shape[0], ptrs, isq, k,
+                                                   fq_field, log_m, offset, int(trace_bitrev), int(out_bitrev), _ptr(out)))
+
+    def poly_eval(self, coeffs, field, n, ncols, points, col_stride=None):
+        """horner_evaluate of every column at every point (get_ood_evals, src/composer.rs:43-86).
+        points: (k, 3) Montgomery words; returns (ncols, k, 3) numpy uint64."""
+        pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 3)
+        out = np.empty((ncols, pts.shape[0], 3), dtype=np.uint64)
+        self._ck(self.lib.ms_poly_eval(self.h, field, _ptr(coeffs), n if col_stride is None else col_stride, ncols, n,
+                                       pts.ctypes.data, pts.shape[0], out.ctypes.data))
+        return out
 
     def fill_random(self, dst, nwords, seed):
         self._ck(self.lib.ms_fill_random(self.h, _ptr(dst), nwords, seed))

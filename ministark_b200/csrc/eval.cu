@@ -35,13 +35,11 @@ struct EvalParams {
     const uint4 *prog;
     u32 nprog;
     const u64 *consts;          // [k][3] Montgomery words
-    const u64 *base_cols;       // Fp columns
-    u64 base_stride;            // words
-    const u64 *ext_cols;        // Fq columns (fq_words each)
-    u64 ext_stride;             // words
+    const u64 *const *col_ptr;  // one device pointer per column (base columns first, then Fq columns)
     u32 fq_words;               // 1: Fq = Fp, 3: Fq = Fq3
     u32 log_m;                  // ce domain size M = 2^log_m
     u32 trace_bitrev;
+    u32 out_bitrev;             // store the result at the storage position t instead of the point index i
     const u64 *tw_lo, *tw_hi;   // g_M^e two-level table
     u32 hi_len;
     u64 offset;                 // domain offset h (Montgomery)
@@ -78,12 +76,13 @@ __global__ void __launch_bounds__(128) eval_kernel(const EvalParams p) {
             case OP_TRACE: {
                 u64 pos = (i + (u64)ins.w) & (M - 1);
                 if (p.trace_bitrev && lm) pos = __brevll(pos) >> (64 - lm);
-                if ((ins.x >> 8) & 1) {  // extension column
-                    const u64 *c = p.ext_cols + (u64)ins.z * p.ext_stride + pos * p.fq_words;
+                const u64 *col = p.col_ptr[ins.z];
+                if ((ins.x >> 8) & 1) {  // Fq column
+                    const u64 *c = col + pos * p.fq_words;
                     r[d][0] = c[0];
                     if (fq3) { r[d][1] = c[1]; r[d][2] = c[2]; }
                 } else {
-                    r[d][0] = p.base_cols[(u64)ins.z * p.base_stride + pos];
+                    r[d][0] = col[pos];
                 }
                 break;
             }
@@ -142,7 +141,7 @@ __global__ void __launch_bounds__(128) eval_kernel(const EvalParams p) {
                 break;
             }
             case OP_STORE: {
-                u64 *o = p.out + i * p.fq_words;
+                u64 *o = p.out + (p.out_bitrev ? t : i) * p.fq_words;
                 o[0] = r[ins.z][0];
                 if (fq3) {
                     o[1] = qa ? r[ins.z][1] : 0;
@@ -159,47 +158,36 @@ __global__ void __launch_bounds__(128) eval_kernel(const EvalParams p) {
 
 using namespace ms;
 
-extern "C" int ms_eval_constraints(ms_ctx *c, const uint32_t *program, unsigned nprog, const uint64_t *consts,
-                                   unsigned nconsts, const void *base_cols, size_t base_stride_elems, unsigned nbase,
-                                   const void *ext_cols, size_t ext_stride_elems, unsigned next, int fq_field,
-                                   unsigned log_m, uint64_t offset_mont, int trace_bitrev, void *out) {
-    if (!c || !program || !consts || !out || nprog == 0) return MS_ERR_INVALID;
-    if (fq_field != MS_FIELD_FP && fq_field != MS_FIELD_FQ3) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: bad Fq field id");
-    if (log_m > 32) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: domain too large");
-    if (offset_mont >= gl::P || offset_mont == 0) return fail(c, MS_ERR_INVALID, "offset must be a non-zero canonical word");
+static int eval_launch(ms_ctx *c, const uint32_t *program, unsigned nprog, const uint64_t *consts, unsigned nconsts,
+                       const std::vector<const u64 *> &cols, const std::vector<int> &col_is_q, int fq_field, unsigned log_m,
+                       uint64_t offset_mont, int trace_bitrev, int out_bitrev, u64 *out_dev) {
     const size_t M = (size_t)1 << log_m;
-    // validate the program against the register file, constant pool and column counts
+    // validate the program against the register file, constant pool and column table
     for (unsigned k = 0; k < nprog; k++) {
         const uint32_t *ins = program + 4 * k;
         const uint32_t op = ins[0] & 0xff;
         if (op > OP_STORE || ins[1] >= (uint32_t)kMaxRegs) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: bad instruction %u", k);
         if (op == OP_CONST && ins[2] >= nconsts) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: constant index out of range");
         if (op == OP_TRACE) {
-            const bool is_q = (ins[0] >> 8) & 1;
-            if (ins[2] >= (is_q ? next : nbase)) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: column %u out of range", ins[2]);
-            if ((is_q ? ext_cols : base_cols) == nullptr) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: missing columns");
+            const int is_q = (ins[0] >> 8) & 1;
+            if (ins[2] >= cols.size()) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: column %u out of range", ins[2]);
+            if (col_is_q[ins[2]] != is_q) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: column %u has the wrong field", ins[2]);
         }
         if ((op == OP_NEG || op == OP_ADD || op == OP_MUL || op == OP_INV || op == OP_POW || op == OP_STORE) &&
             ins[2] >= (uint32_t)kMaxRegs)
             return fail(c, MS_ERR_INVALID, "ms_eval_constraints: bad register");
         if ((op == OP_ADD || op == OP_MUL) && ins[3] >= (uint32_t)kMaxRegs) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: bad register");
     }
-    if (nbase > 1 && base_stride_elems < M) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: base stride < domain");
-    if (next > 1 && ext_stride_elems < M) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: ext stride < domain");
-    // the program and constants are tiny: always copy them to the device
+    // program, constants and the column pointer table are tiny: always copied to the device
     void *meta;
-    const size_t prog_bytes = (size_t)nprog * 16, const_bytes = (size_t)nconsts * 24;
-    int rc = scratch_get(c, 3, prog_bytes + const_bytes + 64, &meta);
+    const size_t prog_bytes = (size_t)nprog * 16, const_bytes = (size_t)nconsts * 24, ptr_bytes = cols.size() * 8;
+    int rc = scratch_get(c, 3, prog_bytes + const_bytes + ptr_bytes + 64, &meta);
     if (rc) return rc;
     MS_CUDA(c, cudaMemcpyAsync(meta, program, prog_bytes, cudaMemcpyDefault, c->stream));
     MS_CUDA(c, cudaMemcpyAsync((char *)meta + prog_bytes, consts, const_bytes, cudaMemcpyDefault, c->stream));
+    if (ptr_bytes)
+        MS_CUDA(c, cudaMemcpyAsync((char *)meta + prog_bytes + const_bytes, cols.data(), ptr_bytes, cudaMemcpyHostToDevice, c->stream));
     MS_CUDA(c, cudaStreamSynchronize(c->stream));  // the host buffers may be temporaries of the caller
-    Staged B(c, nbase ? base_cols : nullptr, nbase ? ((size_t)(nbase - 1) * base_stride_elems + M) * 8 : 0, true, false);
-    if (B.rc) return B.rc;
-    Staged E(c, next ? ext_cols : nullptr, next ? ((size_t)(next - 1) * ext_stride_elems + M) * fq_field * 8 : 0, true, false);
-    if (E.rc) return E.rc;
-    Staged O(c, out, M * fq_field * 8, false, true);
-    if (O.rc) return O.rc;
     const u64 *tw_lo, *tw_hi;
     u32 hi_len;
     if ((rc = ntt_plan_tables(c, log_m, &tw_lo, &tw_hi, &hi_len))) return rc;
@@ -207,22 +195,71 @@ extern "C" int ms_eval_constraints(ms_ctx *c, const uint32_t *program, unsigned 
     p.prog = (const uint4 *)meta;
     p.nprog = nprog;
     p.consts = (const u64 *)((char *)meta + prog_bytes);
-    p.base_cols = B.as<u64>();
-    p.base_stride = base_stride_elems;
-    p.ext_cols = E.as<u64>();
-    p.ext_stride = ext_stride_elems * fq_field;
+    p.col_ptr = (const u64 *const *)((char *)meta + prog_bytes + const_bytes);
     p.fq_words = (u32)fq_field;
     p.log_m = log_m;
     p.trace_bitrev = trace_bitrev ? 1 : 0;
+    p.out_bitrev = (out_bitrev && trace_bitrev) ? 1 : 0;
     p.tw_lo = tw_lo;
     p.tw_hi = tw_hi;
     p.hi_len = hi_len;
     p.offset = offset_mont;
-    p.out = O.as<u64>();
+    p.out = out_dev;
     eval_kernel<<<(unsigned)((M + 127) / 128), 128, 0, c->stream>>>(p);
     c->launches++;
     MS_CHECK_LAUNCH(c);
+    return MS_OK;
+}
+
+extern "C" int ms_eval_constraints(ms_ctx *c, const uint32_t *program, unsigned nprog, const uint64_t *consts,
+                                   unsigned nconsts, const void *base_cols, size_t base_stride_elems, unsigned nbase,
+                                   const void *ext_cols, size_t ext_stride_elems, unsigned next, int fq_field,
+                                   unsigned log_m, uint64_t offset_mont, int trace_bitrev, int out_bitrev, void *out) {
+    if (!c || !program || !consts || !out || nprog == 0) return MS_ERR_INVALID;
+    if (fq_field != MS_FIELD_FP && fq_field != MS_FIELD_FQ3) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: bad Fq field id");
+    if (log_m > 32) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: domain too large");
+    if (offset_mont >= gl::P || offset_mont == 0) return fail(c, MS_ERR_INVALID, "offset must be a non-zero canonical word");
+    const size_t M = (size_t)1 << log_m;
+    if ((nbase && !base_cols) || (next && !ext_cols)) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: missing columns");
+    if (nbase > 1 && base_stride_elems < M) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: base stride < domain");
+    if (next > 1 && ext_stride_elems < M) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: ext stride < domain");
+    Staged B(c, nbase ? base_cols : nullptr, nbase ? ((size_t)(nbase - 1) * base_stride_elems + M) * 8 : 0, true, false);
+    if (B.rc) return B.rc;
+    Staged E(c, next ? ext_cols : nullptr, next ? ((size_t)(next - 1) * ext_stride_elems + M) * fq_field * 8 : 0, true, false);
+    if (E.rc) return E.rc;
+    Staged O(c, out, M * fq_field * 8, false, true);
+    if (O.rc) return O.rc;
+    std::vector<const u64 *> cols;
+    std::vector<int> isq;
+    for (unsigned i = 0; i < nbase; i++) { cols.push_back(B.as<u64>() + (size_t)i * base_stride_elems); isq.push_back(0); }
+    for (unsigned i = 0; i < next; i++) { cols.push_back(E.as<u64>() + (size_t)i * ext_stride_elems * fq_field); isq.push_back(1); }
+    int rc = eval_launch(c, program, nprog, consts, nconsts, cols, isq, fq_field, log_m, offset_mont, trace_bitrev, out_bitrev,
+                         O.as<u64>());
+    if (rc) return rc;
     if ((rc = B.finish())) return rc;
     if ((rc = E.finish())) return rc;
     return O.finish();
+}
+
+// Same evaluator over an explicit table of DEVICE column pointers (columns living in different matrices:
+// base trace LDE, extension trace LDE, composition trace LDE — as the DEEP composition needs).
+// col_fields[i] = MS_FIELD_FP for a base-field column, anything else = a column of `fq_field` elements.
+extern "C" int ms_eval_constraints_ptrs(ms_ctx *c, const uint32_t *program, unsigned nprog, const uint64_t *consts,
+                                        unsigned nconsts, const void *const *col_ptrs, const int *col_is_fq, unsigned ncols,
+                                        int fq_field, unsigned log_m, uint64_t offset_mont, int trace_bitrev, int out_bitrev,
+                                        void *out) {
+    if (!c || !program || !consts || !out || nprog == 0 || (ncols && (!col_ptrs || !col_is_fq))) return MS_ERR_INVALID;
+    if (fq_field != MS_FIELD_FP && fq_field != MS_FIELD_FQ3) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: bad Fq field id");
+    if (log_m > 32) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: domain too large");
+    if (offset_mont >= gl::P || offset_mont == 0) return fail(c, MS_ERR_INVALID, "offset must be a non-zero canonical word");
+    std::vector<const u64 *> cols;
+    std::vector<int> isq;
+    for (unsigned i = 0; i < ncols; i++) {
+        if (!col_ptrs[i] || !is_device_ptr(col_ptrs[i])) return fail(c, MS_ERR_INVALID, "ms_eval_constraints_ptrs: column %u is not a device pointer", i);
+        cols.push_back((const u64 *)col_ptrs[i]);
+        isq.push_back(col_is_fq[i] ? 1 : 0);
+    }
+    if (!is_device_ptr(out)) return fail(c, MS_ERR_INVALID, "ms_eval_constraints_ptrs: out must be a device pointer");
+    return eval_launch(c, program, nprog, consts, nconsts, cols, isq, fq_field, log_m, offset_mont, trace_bitrev, out_bitrev,
+                       (u64 *)out);
 }

@@ -148,7 +148,7 @@ class Program:
         return self.code.shape[0]
 
 
-def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, log_ce=None):
+def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, log_ce=None, fold_pow0=True):
     """Flatten `expr` into the evaluator's linear program.
 
     challenges / hints: extension elements as 3-tuples (or ints) of canonical integers, substituted
@@ -286,7 +286,7 @@ def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, lo
             if log_ce is not None:
                 shift %= (1 << log_ce)
             r = alloc()
-            code.append([OP_TRACE | (int(is_q) << 8), r, col - (num_base_cols if is_q else 0), shift & 0xFFFFFFFF])
+            code.append([OP_TRACE | (int(is_q) << 8), r, col, shift & 0xFFFFFFFF])
         elif k == "neg":
             ra = operand(a[0])
             release(a[0], idx)
