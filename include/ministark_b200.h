@@ -130,6 +130,21 @@ int ms_merkle_nodes_sha256(ms_ctx *ctx, const void *leaves, size_t n, void *node
 int ms_merkle_commit_sha256(ms_ctx *ctx, int field, const void *cols, size_t col_stride_elems, unsigned ncols,
                             size_t nrows, void *leaves, void *nodes, void *root);
 
+/* commitment of a ROW-MAJOR matrix (nrows rows of row_words contiguous words): a FRI layer commits rows of
+ * ff consecutive evaluations (src/fri.rs:199-216, Matrix::from_arrays + from_matrix) — hashed in place */
+int ms_merkle_commit_rows_sha256(ms_ctx *ctx, const void *rows, unsigned row_words, size_t nrows, void *leaves,
+                                 void *nodes, void *root);
+
+/* ---- matrix plumbing ----
+ * Matrix::from_arrays / from_rows (src/matrix.rs:33-64) and the composition split (src/prover.rs:113-120):
+ * n rows of k elements (row-major) -> k columns of n elements */
+int ms_matrix_from_rows(ms_ctx *ctx, int field, const void *rows, size_t n, unsigned k, void *cols,
+                        size_t col_stride_elems);
+/* Matrix::get_row for a list of rows (src/matrix.rs:288-294; Queries::new src/trace.rs:115-157):
+ * out[q * ncols + c] = cols[c][row_ids[q]]; row_ids is a host array */
+int ms_gather_rows(ms_ctx *ctx, int field, const void *cols, size_t col_stride_elems, unsigned ncols, size_t nrows,
+                   const uint64_t *row_ids, unsigned nq, void *out);
+
 /* ---- FRI: apply_drp (src/fri.rs:526-567) evaluated per coset, bit-reversed order in and out ----
  * evals: 2^log_n elements; out: 2^(log_n-log_ff).  alpha: one element of `field`.
  * Equals bit_reverse ∘ NTT ∘ fold ∘ (·ff) ∘ iNTT ∘ bit_reverse of the reference, in one pass. */

@@ -161,6 +161,23 @@ class Context:
                                                   _ptr(leaves), _ptr(nodes), root.ctypes.data))
         return root.tobytes()
 
+    def merkle_commit_rows(self, rows, row_words, nrows, leaves=None, nodes=None):
+        """commit a row-major matrix (a FRI layer: rows of ff consecutive evaluations, src/fri.rs:199-216)"""
+        root = np.zeros(32, dtype=np.uint8)
+        self._ck(self.lib.ms_merkle_commit_rows_sha256(self.h, _ptr(rows), row_words, nrows, _ptr(leaves), _ptr(nodes),
+                                                       root.ctypes.data))
+        return root.tobytes()
+
+    def matrix_from_rows(self, rows, cols, field, n, k, col_stride=None):
+        self._ck(self.lib.ms_matrix_from_rows(self.h, field, _ptr(rows), n, k, _ptr(cols), n if col_stride is None else col_stride))
+
+    def gather_rows(self, cols, field, nrows, ncols, row_ids, col_stride=None):
+        ids = np.ascontiguousarray(row_ids, dtype=np.uint64)
+        out = np.empty((ids.size, ncols * field), dtype=np.uint64)
+        self._ck(self.lib.ms_gather_rows(self.h, field, _ptr(cols), nrows if col_stride is None else col_stride, ncols,
+                                         nrows, ids.ctypes.data, ids.size, out.ctypes.data))
+        return out
+
     # ---- FRI
     def fri_fold(self, evals, out, field, log_n, log_ff, alpha, offset=ONE):
         a = np.ascontiguousarray(alpha, dtype=np.uint64)

@@ -218,4 +218,38 @@ int ms_merkle_commit_sha256(ms_ctx *c, int field, const void *cols, size_t col_s
     return nout.finish();
 }
 
+
+// Commitment of a ROW-MAJOR matrix (nrows rows of row_words contiguous words): FRI layers commit rows of
+// `ff` consecutive evaluations (src/fri.rs:199-216 builds Matrix::from_arrays(chunks) only to hash those
+// rows again); hashing the codeword in place gives the same leaves without the transpose.
+int ms_merkle_commit_rows_sha256(ms_ctx *c, const void *rows, unsigned row_words, size_t nrows, void *leaves, void *nodes,
+                                 void *root) {
+    if (!c || !rows || !root || row_words == 0) return MS_ERR_INVALID;
+    if (nrows < 2 || (nrows & (nrows - 1))) return fail(c, MS_ERR_INVALID, "merkle tree needs a power-of-two number of leaves >= 2, got %zu", nrows);
+    Staged in(c, rows, nrows * row_words * 8, true, false);
+    if (in.rc) return in.rc;
+    int rc;
+    void *lv = nullptr, *nd = nullptr;
+    Staged lout(c, leaves, leaves ? nrows * 32 : 0, false, true);
+    if (lout.rc) return lout.rc;
+    Staged nout(c, nodes, nodes ? nrows * 32 : 0, false, true);
+    if (nout.rc) return nout.rc;
+    if (leaves) lv = lout.dev;
+    else if ((rc = scratch_get(c, 2, nrows * 32, &lv))) return rc;
+    if (nodes) nd = nout.dev;
+    else if ((rc = scratch_get(c, 3, nrows * 32, &nd))) return rc;
+    // one "column" whose element is the whole row: word t of row i at base + i*row_words + t
+    const unsigned threads = 128;
+    hash_rows_kernel<<<(unsigned)((nrows + threads - 1) / threads), threads, 0, c->stream>>>(in.as<u64>(), 0, row_words, row_words,
+                                                                                              nrows, (u32 *)lv);
+    c->launches++;
+    MS_CHECK_LAUNCH(c);
+    if ((rc = merkle_nodes_dev(c, (const u32 *)lv, nrows, (u32 *)nd))) return rc;
+    MS_CUDA(c, cudaMemcpyAsync(root, (const char *)nd + 32, 32, cudaMemcpyDefault, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if ((rc = in.finish())) return rc;
+    if ((rc = lout.finish())) return rc;
+    return nout.finish();
+}
+
 }  // extern "C"

@@ -113,6 +113,22 @@ __global__ void sum_columns_kernel(const u64 *cols, size_t col_stride_words, uns
     acc[i] = s;
 }
 
+// dst column c, row i  <-  src row i, entry c   (row-major [n][k] -> column-major [k][n], elements of EW words)
+__global__ void from_rows_kernel(const u64 *src, u64 *dst, size_t n, unsigned k, unsigned ew, size_t dst_col_stride_words) {
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;   // over n * k elements, column-major order
+    if (idx >= n * k) return;
+    const size_t i = idx % n, c = idx / n;
+    for (unsigned w = 0; w < ew; w++) dst[c * dst_col_stride_words + i * ew + w] = src[(i * k + c) * ew + w];
+}
+// out[q][c] = cols[c][rows[q]]
+__global__ void gather_rows_kernel(const u64 *cols, size_t col_stride_words, unsigned ncols, unsigned ew, const u64 *rows,
+                                   unsigned nq, u64 *out) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nq * ncols) return;
+    const unsigned q = idx / ncols, cc = idx % ncols;
+    for (unsigned w = 0; w < ew; w++) out[((size_t)q * ncols + cc) * ew + w] = cols[(size_t)cc * col_stride_words + rows[q] * ew + w];
+}
+
 }  // namespace ms
 
 using namespace ms;
@@ -212,6 +228,56 @@ int ms_sum_columns(ms_ctx *c, int field, const void *cols, size_t col_stride_ele
     int rc;
     if ((rc = in.finish())) return rc;
     return out.finish();
+}
+
+
+// Matrix::from_arrays / from_rows (src/matrix.rs:33-64) and the composition-polynomial split of
+// src/prover.rs:113-120: n rows of k elements (row-major) -> k columns of n elements.
+int ms_matrix_from_rows(ms_ctx *c, int field, const void *rows, size_t n, unsigned k, void *cols, size_t col_stride_elems) {
+    if (!c || !rows || !cols || k == 0) return MS_ERR_INVALID;
+    if (field != 1 && field != 3) return fail(c, MS_ERR_INVALID, "ms_matrix_from_rows: bad field id");
+    if (k > 1 && col_stride_elems < n) return fail(c, MS_ERR_INVALID, "ms_matrix_from_rows: stride < n");
+    if (n == 0) return MS_OK;
+    Staged in(c, rows, n * k * field * 8, true, false);
+    if (in.rc) return in.rc;
+    Staged out(c, cols, ((size_t)(k - 1) * col_stride_elems + n) * field * 8, false, true);
+    if (out.rc) return out.rc;
+    const size_t total = n * k;
+    from_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(in.as<u64>(), out.as<u64>(), n, k, (unsigned)field,
+                                                                              col_stride_elems * field);
+    c->launches++;
+    MS_CHECK_LAUNCH(c);
+    int rc;
+    if ((rc = in.finish())) return rc;
+    return out.finish();
+}
+
+// Matrix::get_row for a list of rows (src/matrix.rs:288-294; Queries::new src/trace.rs:115-157, query_layer
+// src/fri.rs:650-664): out[q * ncols + c] = cols[c][row_ids[q]].  row_ids: host array.
+int ms_gather_rows(ms_ctx *c, int field, const void *cols, size_t col_stride_elems, unsigned ncols, size_t nrows,
+                   const uint64_t *row_ids, unsigned nq, void *out) {
+    if (!c || !cols || !row_ids || !out) return MS_ERR_INVALID;
+    if (field != 1 && field != 3) return fail(c, MS_ERR_INVALID, "ms_gather_rows: bad field id");
+    if (ncols == 0 || nq == 0) return MS_OK;
+    for (unsigned q = 0; q < nq; q++)
+        if (row_ids[q] >= nrows) return fail(c, MS_ERR_INVALID, "ms_gather_rows: row %llu out of range", (unsigned long long)row_ids[q]);
+    if (ncols > 1 && col_stride_elems < nrows) return fail(c, MS_ERR_INVALID, "ms_gather_rows: stride < nrows");
+    Staged in(c, cols, ((size_t)(ncols - 1) * col_stride_elems + nrows) * field * 8, true, false);
+    if (in.rc) return in.rc;
+    Staged o(c, out, (size_t)nq * ncols * field * 8, false, true);
+    if (o.rc) return o.rc;
+    void *ids;
+    int rc = scratch_get(c, 3, (size_t)nq * 8, &ids);
+    if (rc) return rc;
+    MS_CUDA(c, cudaMemcpyAsync(ids, row_ids, (size_t)nq * 8, cudaMemcpyHostToDevice, c->stream));
+    const unsigned total = nq * ncols;
+    gather_rows_kernel<<<(total + 127) / 128, 128, 0, c->stream>>>(in.as<u64>(), col_stride_elems * field, ncols, (unsigned)field,
+                                                                    (const u64 *)ids, nq, o.as<u64>());
+    c->launches++;
+    MS_CHECK_LAUNCH(c);
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if ((rc = in.finish())) return rc;
+    return o.finish();
 }
 
 }  // extern "C"

@@ -196,3 +196,47 @@ def test_fri_layer_sequence_and_commit(ctx, orc):
         want = orc.fri_apply_drp(want, field, ln, log_ff, alpha)
         assert np.array_equal(nxt, want)
         got = nxt
+
+
+# ------------------------------------------------------------------ matrix plumbing + resident FRI layers
+@pytest.mark.parametrize("field,k", [(1, 2), (3, 8), (3, 16)])
+def test_from_rows_and_gather(ctx, orc, field, k):
+    n = 512
+    rows = orc.rand_matrix(1, n * k, field, seed=k)[0]            # n rows of k elements, row-major
+    cols = np.empty((k, n * field), dtype=np.uint64)
+    ctx.matrix_from_rows(rows, cols, field, n, k)
+    want = np.ascontiguousarray(rows.reshape(n, k, field).transpose(1, 0, 2)).reshape(k, -1)
+    assert np.array_equal(cols, want)                              # Matrix::from_arrays (src/matrix.rs:50-64)
+    ids = [0, 5, n - 1, 17, 5]
+    got = ctx.gather_rows(cols, field, n, k, ids)                  # Matrix::get_row (src/matrix.rs:288-294)
+    for q, i in enumerate(ids):
+        assert np.array_equal(got[q], rows.reshape(n, k * field)[i])
+    with pytest.raises(ms.MsError):
+        ctx.gather_rows(cols, field, n, k, [n])
+
+
+@pytest.mark.parametrize("log_n", [12, 20])
+def test_config4_fri_layers_resident(ctx, orc, log_n):
+    """BASELINE config 4 shape: Fq3 codeword, ff = 8 (fib) — each layer committed in place (rows of ff
+    consecutive evaluations) and folded on the device; roots and codewords equal the reference flow
+    Matrix::from_arrays + from_matrix + apply_drp (src/fri.rs:199-231,526-567)."""
+    torch = pytest.importorskip("torch")
+    field, log_ff = 3, 3
+    ev = orc.rand_matrix(1, 1 << log_n, field, seed=log_n)[0]
+    cur = torch.from_numpy(ev.view(np.int64)).cuda()
+    want = ev
+    nlayers = 2 if log_n > 12 else 3
+    for layer in range(nlayers):
+        ln = log_n - layer * log_ff
+        alpha = orc.rand_matrix(1, 1, field, seed=500 + layer)[0]
+        nrows = 1 << (ln - log_ff)
+        root = ctx.merkle_commit_rows(cur, (1 << log_ff) * field, nrows)
+        rows = want.reshape(nrows, (1 << log_ff), field)
+        cols = np.ascontiguousarray(rows.transpose(1, 0, 2)).reshape(1 << log_ff, -1)
+        assert root == orc.merkle_nodes(orc.hash_rows(cols, field))[1].tobytes()
+        nxt = torch.empty((field << ln) >> log_ff, dtype=torch.int64, device="cuda")
+        ctx.fri_fold(cur, nxt, field, ln, log_ff, alpha)
+        ctx.sync()
+        want = orc.fri_apply_drp(want, field, ln, log_ff, alpha)
+        assert np.array_equal(nxt.cpu().numpy().view(np.uint64), want)
+        cur = nxt
