@@ -25,8 +25,42 @@ __constant__ u32 c_K[64] = {
     0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
     0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
 
-__device__ __forceinline__ u32 rotr(u32 x, int r) { return __funnelshift_r(x, x, r); }
 __device__ __forceinline__ u32 bswap(u32 x) { return __byte_perm(x, 0, 0x0123); }
+
+// SHA-256 is bound by the INT32 ALU pipe (SHF/LOP3/IADD3; ncu: 94 % busy with the FMA pipe at 6 %).  The
+// rotations are therefore done on the FMA pipe: x * 2^(32-r) as a 64-bit IMAD.WIDE has x >> r in its high
+// word and x << (32-r) in its low word, and since those two have disjoint bits, rotr(x, r) = hi ^ lo folds
+// into the 3-input XORs of the sigma functions.  ALU-pipe work per compression drops by a quarter.
+template <int R>
+__device__ __forceinline__ void wide_rot(u32 x, u32 &lo, u32 &hi) {
+    unsigned long long p;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(x), "n"(1u << (32 - R)));
+    asm("mov.b64 {%0,%1}, %2;" : "=r"(lo), "=r"(hi) : "l"(p));
+}
+__device__ __forceinline__ u32 big_sigma1(u32 e) {
+    u32 l6, h6, l11, h11, l25, h25;
+    wide_rot<6>(e, l6, h6); wide_rot<11>(e, l11, h11); wide_rot<25>(e, l25, h25);
+    return (l6 ^ h6 ^ l11) ^ (h11 ^ l25 ^ h25);
+}
+__device__ __forceinline__ u32 big_sigma0(u32 a) {
+    u32 l2, h2, l13, h13, l22, h22;
+    wide_rot<2>(a, l2, h2); wide_rot<13>(a, l13, h13); wide_rot<22>(a, l22, h22);
+    return (l2 ^ h2 ^ l13) ^ (h13 ^ l22 ^ h22);
+}
+__device__ __forceinline__ u32 small_sigma0(u32 w) {
+    u32 l7, h7, l18, h18, l3, h3;
+    wide_rot<7>(w, l7, h7); wide_rot<18>(w, l18, h18); wide_rot<3>(w, l3, h3);
+    return (l7 ^ h7 ^ l18) ^ h18 ^ h3;
+}
+__device__ __forceinline__ u32 small_sigma1(u32 w) {
+    u32 l17, h17, l19, h19, l10, h10;
+    wide_rot<17>(w, l17, h17); wide_rot<19>(w, l19, h19); wide_rot<10>(w, l10, h10);
+    return (l17 ^ h17 ^ l19) ^ h19 ^ h10;
+}
+
+// K[i] + W[i] of the constant second block of a 64-byte message (0x80, zeros, bit length 512): the
+// Merkle node hash needs no message schedule for it.
+__constant__ u32 c_KW_pad64[64];
 
 struct Sha {
     u32 h[8];
@@ -39,18 +73,25 @@ struct Sha {
         u32 a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
 #pragma unroll
         for (int i = 0; i < 64; i++) {
-            if (i >= 16) {
-                u32 w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
-                u32 s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3);
-                u32 s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10);
-                w[i & 15] = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
-            }
-            u32 S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
+            if (i >= 16)
+                w[i & 15] = w[i & 15] + small_sigma0(w[(i + 1) & 15]) + w[(i + 9) & 15] + small_sigma1(w[(i + 14) & 15]);
             u32 ch = (e & f) ^ (~e & g);
-            u32 t1 = hh + S1 + ch + c_K[i] + w[i & 15];
-            u32 S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
+            u32 t1 = hh + big_sigma1(e) + ch + c_K[i] + w[i & 15];
             u32 mj = (a & b) ^ (a & c) ^ (b & c);
-            u32 t2 = S0 + mj;
+            u32 t2 = big_sigma0(a) + mj;
+            hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        }
+        h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+    }
+    // compression of the constant padding block that follows a 64-byte message
+    __device__ __forceinline__ void compress_pad64() {
+        u32 a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            u32 ch = (e & f) ^ (~e & g);
+            u32 t1 = hh + big_sigma1(e) + ch + c_KW_pad64[i];
+            u32 mj = (a & b) ^ (a & c) ^ (b & c);
+            u32 t2 = big_sigma0(a) + mj;
             hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
         }
         h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
@@ -117,11 +158,7 @@ __global__ void __launch_bounds__(128) merkle_level_kernel(const u32 *__restrict
         w[4 * q] = bswap(v.x); w[4 * q + 1] = bswap(v.y); w[4 * q + 2] = bswap(v.z); w[4 * q + 3] = bswap(v.w);
     }
     s.compress(w);
-#pragma unroll
-    for (int j = 0; j < 16; j++) w[j] = 0;
-    w[0] = 0x80000000u;
-    w[15] = 512;
-    s.compress(w);
+    s.compress_pad64();
     s.store(dst + k * 8);
 }
 
@@ -136,7 +173,37 @@ static int hash_rows_dev(ms_ctx *c, int field, const u64 *cols, size_t col_strid
     return MS_OK;
 }
 
+static u32 h_rotr(u32 x, int r) { return (x >> r) | (x << (32 - r)); }
+static int upload_pad_schedule(ms_ctx *c) {
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && done[dev]) return MS_OK;
+    static const u32 K[64] = {
+        0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+        0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+        0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+        0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+        0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+        0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+        0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+        0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+    u32 w[64] = {0}, kw[64];
+    w[0] = 0x80000000u;
+    w[15] = 512;
+    for (int i = 16; i < 64; i++) {
+        u32 s0 = h_rotr(w[i - 15], 7) ^ h_rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+        u32 s1 = h_rotr(w[i - 2], 17) ^ h_rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+        w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    for (int i = 0; i < 64; i++) kw[i] = K[i] + w[i];
+    MS_CUDA(c, cudaMemcpyToSymbol(c_KW_pad64, kw, sizeof kw));
+    if (dev < 64) done[dev] = true;
+    return MS_OK;
+}
+
 static int merkle_nodes_dev(ms_ctx *c, const u32 *leaves, size_t n, u32 *nodes) {
+    if (int rc = upload_pad_schedule(c)) return rc;
     MS_CUDA(c, cudaMemsetAsync(nodes, 0, 32, c->stream));
     const unsigned threads = 128;
     // leaf pairs -> nodes[n/2 .. n)
