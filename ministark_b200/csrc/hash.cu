@@ -27,36 +27,14 @@ __constant__ u32 c_K[64] = {
 
 __device__ __forceinline__ u32 bswap(u32 x) { return __byte_perm(x, 0, 0x0123); }
 
-// SHA-256 is bound by the INT32 ALU pipe (SHF/LOP3/IADD3; ncu: 94 % busy with the FMA pipe at 6 %).  The
-// rotations are therefore done on the FMA pipe: x * 2^(32-r) as a 64-bit IMAD.WIDE has x >> r in its high
-// word and x << (32-r) in its low word, and since those two have disjoint bits, rotr(x, r) = hi ^ lo folds
-// into the 3-input XORs of the sigma functions.  ALU-pipe work per compression drops by a quarter.
-template <int R>
-__device__ __forceinline__ void wide_rot(u32 x, u32 &lo, u32 &hi) {
-    unsigned long long p;
-    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(x), "n"(1u << (32 - R)));
-    asm("mov.b64 {%0,%1}, %2;" : "=r"(lo), "=r"(hi) : "l"(p));
-}
-__device__ __forceinline__ u32 big_sigma1(u32 e) {
-    u32 l6, h6, l11, h11, l25, h25;
-    wide_rot<6>(e, l6, h6); wide_rot<11>(e, l11, h11); wide_rot<25>(e, l25, h25);
-    return (l6 ^ h6 ^ l11) ^ (h11 ^ l25 ^ h25);
-}
-__device__ __forceinline__ u32 big_sigma0(u32 a) {
-    u32 l2, h2, l13, h13, l22, h22;
-    wide_rot<2>(a, l2, h2); wide_rot<13>(a, l13, h13); wide_rot<22>(a, l22, h22);
-    return (l2 ^ h2 ^ l13) ^ (h13 ^ l22 ^ h22);
-}
-__device__ __forceinline__ u32 small_sigma0(u32 w) {
-    u32 l7, h7, l18, h18, l3, h3;
-    wide_rot<7>(w, l7, h7); wide_rot<18>(w, l18, h18); wide_rot<3>(w, l3, h3);
-    return (l7 ^ h7 ^ l18) ^ h18 ^ h3;
-}
-__device__ __forceinline__ u32 small_sigma1(u32 w) {
-    u32 l17, h17, l19, h19, l10, h10;
-    wide_rot<17>(w, l17, h17); wide_rot<19>(w, l19, h19); wide_rot<10>(w, l10, h10);
-    return (l17 ^ h17 ^ l19) ^ h19 ^ h10;
-}
+// SHA-256 is bound by the INT32 ALU pipe (SHF/LOP3/IADD3; ncu: 94 % busy).  Moving the rotations to the FMA
+// pipe (x * 2^(32-r) as IMAD.WIDE, hi ^ lo) was measured and is SLOWER on sm_100a (84.7 ms vs 68.1 ms for the
+// config-3 commit: IMAD.WIDE issues at half rate and the instruction count grows), so they stay funnel shifts.
+__device__ __forceinline__ u32 rotr(u32 x, int r) { return __funnelshift_r(x, x, r); }
+__device__ __forceinline__ u32 big_sigma1(u32 e) { return rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25); }
+__device__ __forceinline__ u32 big_sigma0(u32 a) { return rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22); }
+__device__ __forceinline__ u32 small_sigma0(u32 w) { return rotr(w, 7) ^ rotr(w, 18) ^ (w >> 3); }
+__device__ __forceinline__ u32 small_sigma1(u32 w) { return rotr(w, 17) ^ rotr(w, 19) ^ (w >> 10); }
 
 // K[i] + W[i] of the constant second block of a 64-byte message (0x80, zeros, bit length 512): the
 // Merkle node hash needs no message schedule for it.

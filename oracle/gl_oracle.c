@@ -160,9 +160,13 @@ u64 orc_generator(void) { return fp_from_canon(7); }
 
 /* --------------------------------------------------------- bit reverse -- */
 static inline size_t bitrev(size_t i, unsigned log_n) {
-    size_t r = 0;
-    for (unsigned b = 0; b < log_n; b++) r |= ((i >> b) & 1) << (log_n - 1 - b);
-    return r;
+    if (log_n == 0) return 0;
+    u64 x = (u64)i;
+    x = ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+    x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+    x = __builtin_bswap64(x);
+    return (size_t)(x >> (64 - log_n));
 }
 /* gpu/src/utils.rs:4-11,32-42.  elem_words = 1 (Fp) or 3 (Fq3). */
 void orc_bit_reverse(u64 *v, unsigned elem_words, unsigned log_n) {
@@ -193,18 +197,32 @@ static u64 *roots_table(u64 root, size_t half) {
 static void dif_levels(u64 *a, unsigned lanes, unsigned log_n, const u64 *roots, int par) {
     size_t n = (size_t)1 << log_n;
     for (size_t gap = n >> 1; gap >= 1; gap >>= 1) {
-        size_t step = (n >> 1) / gap;
-        size_t nblk = n / (2 * gap);
-        #pragma omp parallel for if (par) schedule(static)
-        for (size_t t = 0; t < (n >> 1); t++) {
-            size_t blk = t / gap, j = t % gap;
-            (void)nblk;
-            u64 w = roots[j * step];
-            u64 *lo = a + (blk * 2 * gap + j) * lanes, *hi = lo + gap * lanes;
-            for (unsigned l = 0; l < lanes; l++) {
-                u64 u = lo[l], v = hi[l];
-                lo[l] = fp_add(u, v);
-                hi[l] = fp_mul(fp_sub(u, v), w);
+        const size_t step = (n >> 1) / gap, nblk = n / (2 * gap);
+        if (nblk >= 64 || !par) {
+            #pragma omp parallel for if (par) schedule(static)
+            for (size_t blk = 0; blk < nblk; blk++) {
+                u64 *lo = a + blk * 2 * gap * lanes, *hi = lo + gap * lanes;
+                for (size_t j = 0; j < gap; j++) {
+                    const u64 w = roots[j * step];
+                    for (unsigned l = 0; l < lanes; l++) {
+                        const u64 u = lo[j * lanes + l], v = hi[j * lanes + l];
+                        lo[j * lanes + l] = fp_add(u, v);
+                        hi[j * lanes + l] = fp_mul(fp_sub(u, v), w);
+                    }
+                }
+            }
+        } else {
+            for (size_t blk = 0; blk < nblk; blk++) {
+                u64 *lo = a + blk * 2 * gap * lanes, *hi = lo + gap * lanes;
+                #pragma omp parallel for schedule(static)
+                for (size_t j = 0; j < gap; j++) {
+                    const u64 w = roots[j * step];
+                    for (unsigned l = 0; l < lanes; l++) {
+                        const u64 u = lo[j * lanes + l], v = hi[j * lanes + l];
+                        lo[j * lanes + l] = fp_add(u, v);
+                        hi[j * lanes + l] = fp_mul(fp_sub(u, v), w);
+                    }
+                }
             }
         }
     }
@@ -214,16 +232,32 @@ static void dif_levels(u64 *a, unsigned lanes, unsigned log_n, const u64 *roots,
 static void dit_levels(u64 *a, unsigned lanes, unsigned log_n, const u64 *roots, size_t start_gap, int par) {
     size_t n = (size_t)1 << log_n;
     for (size_t gap = start_gap; gap < n; gap <<= 1) {
-        size_t step = (n >> 1) / gap;
-        #pragma omp parallel for if (par) schedule(static)
-        for (size_t t = 0; t < (n >> 1); t++) {
-            size_t blk = t / gap, j = t % gap;
-            u64 w = roots[j * step];
-            u64 *lo = a + (blk * 2 * gap + j) * lanes, *hi = lo + gap * lanes;
-            for (unsigned l = 0; l < lanes; l++) {
-                u64 u = lo[l], v = fp_mul(hi[l], w);
-                lo[l] = fp_add(u, v);
-                hi[l] = fp_sub(u, v);
+        const size_t step = (n >> 1) / gap, nblk = n / (2 * gap);
+        if (nblk >= 64 || !par) {
+            #pragma omp parallel for if (par) schedule(static)
+            for (size_t blk = 0; blk < nblk; blk++) {
+                u64 *lo = a + blk * 2 * gap * lanes, *hi = lo + gap * lanes;
+                for (size_t j = 0; j < gap; j++) {
+                    const u64 w = roots[j * step];
+                    for (unsigned l = 0; l < lanes; l++) {
+                        const u64 u = lo[j * lanes + l], v = fp_mul(hi[j * lanes + l], w);
+                        lo[j * lanes + l] = fp_add(u, v);
+                        hi[j * lanes + l] = fp_sub(u, v);
+                    }
+                }
+            }
+        } else {
+            for (size_t blk = 0; blk < nblk; blk++) {
+                u64 *lo = a + blk * 2 * gap * lanes, *hi = lo + gap * lanes;
+                #pragma omp parallel for schedule(static)
+                for (size_t j = 0; j < gap; j++) {
+                    const u64 w = roots[j * step];
+                    for (unsigned l = 0; l < lanes; l++) {
+                        const u64 u = lo[j * lanes + l], v = fp_mul(hi[j * lanes + l], w);
+                        lo[j * lanes + l] = fp_add(u, v);
+                        hi[j * lanes + l] = fp_sub(u, v);
+                    }
+                }
             }
         }
     }
@@ -329,7 +363,68 @@ static const u32 K256[64] = {
     0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
     0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
 static inline u32 rotr(u32 x, int r) { return (x >> r) | (x << (32 - r)); }
-static void sha256_block(u32 st[8], const uint8_t *blk) {
+
+/* The reference's sha2 0.10.8 selects the SHA-NI backend at run time on x86-64 (cpufeatures); for a fair
+ * CPU baseline the oracle does the same.  Standard SHA extensions schedule: state kept as ABEF / CDGH. */
+#if defined(__x86_64__)
+#include <cpuid.h>
+#include <immintrin.h>
+static int have_sha_ni(void) {
+    static int cached = -1;
+    if (cached < 0) {
+        unsigned a, b, c, d;
+        cached = (__get_cpuid_count(7, 0, &a, &b, &c, &d) && (b & (1u << 29))) ? 1 : 0;
+        if (getenv("ORACLE_NO_SHA_NI")) cached = 0;
+    }
+    return cached;
+}
+__attribute__((target("sha,sse4.1,ssse3")))
+static void sha256_block_ni(u32 st[8], const uint8_t *blk) {
+    const __m128i mask = _mm_set_epi64x(0x0c0d0e0f08090a0bULL, 0x0405060700010203ULL);
+    __m128i tmp = _mm_loadu_si128((const __m128i *)&st[0]);
+    __m128i s1 = _mm_loadu_si128((const __m128i *)&st[4]);
+    tmp = _mm_shuffle_epi32(tmp, 0xB1);
+    s1 = _mm_shuffle_epi32(s1, 0x1B);
+    __m128i s0 = _mm_alignr_epi8(tmp, s1, 8);
+    s1 = _mm_blend_epi16(s1, tmp, 0xF0);
+    const __m128i save0 = s0, save1 = s1;
+    __m128i m[4];
+    for (int g = 0; g < 16; g++) {
+        __m128i w;
+        if (g < 4) {
+            w = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(blk + 16 * g)), mask);
+        } else {
+            __m128i t = _mm_add_epi32(_mm_sha256msg1_epu32(m[0], m[1]), _mm_alignr_epi8(m[3], m[2], 4));
+            w = _mm_sha256msg2_epu32(t, m[3]);
+            m[0] = m[1]; m[1] = m[2]; m[2] = m[3];
+        }
+        m[g < 4 ? g : 3] = w;
+        __m128i msg = _mm_add_epi32(w, _mm_loadu_si128((const __m128i *)&K256[4 * g]));
+        s1 = _mm_sha256rnds2_epu32(s1, s0, msg);
+        msg = _mm_shuffle_epi32(msg, 0x0E);
+        s0 = _mm_sha256rnds2_epu32(s0, s1, msg);
+    }
+    s0 = _mm_add_epi32(s0, save0);
+    s1 = _mm_add_epi32(s1, save1);
+    tmp = _mm_shuffle_epi32(s0, 0x1B);
+    s1 = _mm_shuffle_epi32(s1, 0xB1);
+    s0 = _mm_blend_epi16(tmp, s1, 0xF0);
+    s1 = _mm_alignr_epi8(s1, tmp, 8);
+    _mm_storeu_si128((__m128i *)&st[0], s0);
+    _mm_storeu_si128((__m128i *)&st[4], s1);
+}
+#else
+static int have_sha_ni(void) { return 0; }
+static void sha256_block_ni(u32 st[8], const uint8_t *blk) { (void)st; (void)blk; }
+#endif
+int orc_have_sha_ni(void) { return have_sha_ni(); }
+
+static void sha256_block_portable(u32 st[8], const uint8_t *blk);
+static inline void sha256_block(u32 st[8], const uint8_t *blk) {
+    if (have_sha_ni()) sha256_block_ni(st, blk);
+    else sha256_block_portable(st, blk);
+}
+static void sha256_block_portable(u32 st[8], const uint8_t *blk) {
     u32 w[64];
     for (int i = 0; i < 16; i++)
         w[i] = ((u32)blk[4 * i] << 24) | ((u32)blk[4 * i + 1] << 16) | ((u32)blk[4 * i + 2] << 8) | blk[4 * i + 3];
@@ -421,9 +516,47 @@ static fq3 load_el(const u64 *p, unsigned f, size_t i) {
 static void store_el(u64 *p, unsigned f, size_t i, fq3 v) {
     if (f == 1) p[i] = v.c[0]; else memcpy(p + 3 * i, &v, 24);
 }
+/* batch inversion over chunks of 512 elements, as eval_cpu.rs:280-295 / ark_ff::batch_inversion does:
+ * one field inversion per chunk + 3 multiplications per element (zeros are skipped and stay zero) */
+static void batch_inverse(unsigned field, u64 *dst, const u64 *src, size_t n) {
+    const size_t CH = 512;
+    size_t nch = (n + CH - 1) / CH;
+    #pragma omp parallel for schedule(static)
+    for (size_t ch = 0; ch < nch; ch++) {
+        size_t s0 = ch * CH, e0 = s0 + CH < n ? s0 + CH : n;
+        fq3 pref[512];
+        fq3 acc = fq3_one();
+        for (size_t i = s0; i < e0; i++) {
+            fq3 v = load_el(src, field, i);
+            int z = (v.c[0] | v.c[1] | v.c[2]) == 0;
+            pref[i - s0] = acc;
+            if (!z) acc = fq3_mul(acc, v);
+        }
+        fq3 inv = (field == 1) ? fq3_from_fp(fp_inv(acc.c[0])) : fq3_inv(acc);
+        for (size_t i = e0; i-- > s0;) {
+            fq3 v = load_el(src, field, i);
+            int z = (v.c[0] | v.c[1] | v.c[2]) == 0;
+            if (z) { store_el(dst, field, i, fq3_zero()); continue; }
+            store_el(dst, field, i, fq3_mul(inv, pref[i - s0]));
+            inv = fq3_mul(inv, v);
+        }
+    }
+}
+
 /* dst[i] = lhs[i] OP rhs[(i+shift)%n]   (MulInto/AddInto; *Assign when dst==lhs) */
 void orc_pointwise(int op, unsigned dfield, u64 *dst, unsigned lfield, const u64 *lhs,
                    unsigned rfield, const u64 *rhs, size_t n, size_t shift, u64 exponent) {
+    if (op == OP_INV && dfield == lfield) {
+        if (dst == lhs) {
+            u64 *tmp = (u64 *)malloc(sizeof(u64) * n * lfield);
+            memcpy(tmp, lhs, sizeof(u64) * n * lfield);
+            batch_inverse(lfield, dst, tmp, n);
+            free(tmp);
+        } else {
+            batch_inverse(lfield, dst, lhs, n);
+        }
+        return;
+    }
     #pragma omp parallel for schedule(static)
     for (size_t i = 0; i < n; i++) {
         fq3 a = load_el(lhs, lfield, i), r;
