@@ -61,26 +61,48 @@ __device__ __forceinline__ u64 tw_lookup(const u64 *lo, const u64 *hi, u32 hi_le
 }
 
 // One radix-2^B step of the CTA-level sub-NTT.  f = bit position of the field inside the linear
-// tile index (r * W + c); lbits = number of r-bits below the field; iR_* describe the fields
-// already transformed (needed by the last step only).
-template <int B, bool INV, bool FIRST, bool LAST, int B1, int B2, int LOGR>
-__device__ __forceinline__ void do_step(u64 *sm, const PassParams &p, const Tables &tb, const TileCtx &tc,
-                                        const int f, const int lbits) {
+// tile index (r * W + c); lbits = number of r-bits below the field; B1/B2 describe the fields
+// already transformed (needed by the last step only).  LW >= 0 fixes log2(W) at compile time so all
+// shared-memory offsets fold into immediates.
+//   din : the first step reads its 16 inputs straight from global memory (lane-contiguous tiles), the
+//         coset pre-scale factor is applied on the way in;
+//   dout: the last step writes its 16 outputs straight to global memory.
+template <int B, bool INV, bool FIRST, bool LAST, int B1, int B2, int LOGR, int LW>
+__device__ __forceinline__ void do_step(u64 *sm, const PassParams &p, const Tables &tb, const TileCtx &tc, const int f,
+                                        const int lbits, const bool din, const bool dout, const u64 *__restrict__ src,
+                                        u64 *__restrict__ dst) {
     constexpr int RAD = 1 << B;
     constexpr int G = kElemsPerThread >> B;
+    const int lw = LW >= 0 ? LW : (int)p.log_w;
     const u32 nthreads = blockDim.x, tid = threadIdx.x;
-    const u32 wmask = (1u << p.log_w) - 1;
+    const u32 wmask = (1u << lw) - 1;
+    const u32 es = p.estride;
 #pragma unroll 1
     for (int gi = 0; gi < G; gi++) {
         const u32 g = gi * nthreads + tid;
         const u32 i0 = ((g >> f) << (f + B)) | (g & ((1u << f) - 1));
-        const u32 c = i0 & wmask, rpos0 = i0 >> p.log_w;
+        const u32 c = i0 & wmask, rpos0 = i0 >> lw;
         u64 x[RAD];
-        static_for<0, RAD>([&](auto K) { x[K] = sm[padi(i0 + ((u32)K << f))]; });
+        if (FIRST && din) {
+            // rows rpos0 + (K << (f - lw)), lane c: 16 coalesced global loads (2 x 128 B per warp each)
+            const u64 e0 = tc.in_base + (u64)rpos0 * p.in_rs + (u64)c * p.in_cs;
+            const u64 stj = p.in_rs << (f - lw);
+            if (p.has_pre && tc.pre_tab) {
+                u64 tw[RAD];
+                static_for<0, RAD>([&](auto K) {
+                    x[K] = src[(e0 + (u64)K * stj) * es];
+                    tw[K] = __ldg(tc.pre_tab + e0 + (u64)K * stj);
+                });
+                static_for<0, RAD>([&](auto K) { x[K] = mul(x[K], tw[K]); });
+            } else {
+                static_for<0, RAD>([&](auto K) { x[K] = src[(e0 + (u64)K * stj) * es]; });
+            }
+        } else {
+            static_for<0, RAD>([&](auto K) { x[K] = sm[padi(i0 + ((u32)K << f))]; });
+        }
 
         if (FIRST && p.has_pre && !tc.pre_tab) {
-            // (with a full pre-scale table the factor was applied while loading the tile)
-            // x[k] *= q^(in index), in index = A + k * (in_rs << (f - log_w))
+            // no full table: x[k] *= q^(in index), in index = A + k * (in_rs << (f - lw)), as a progression
             u64 A = tc.in_base + (u64)rpos0 * p.in_rs + (u64)c * p.in_cs;
             u64 t = tw_lookup(tc.sc_lo, tc.sc_hi, p.hi_len, A);
             static_for<0, RAD>([&](auto K) {
@@ -91,6 +113,7 @@ __device__ __forceinline__ void do_step(u64 *sm, const PassParams &p, const Tabl
 
         dft_regs<B, INV>(x);
 
+        u32 iR0 = 0;
         if (!LAST) {
             // inner twiddle omega_{R_m}^(kappa * rlow), R_m = 2^(lbits+B)
             const u32 rlow = rpos0 & ((1u << lbits) - 1);
@@ -102,7 +125,6 @@ __device__ __forceinline__ void do_step(u64 *sm, const PassParams &p, const Tabl
             x[0] = canon(x[0]);
         } else {
             // output index of this pass's digit contributed by the earlier fields
-            u32 iR0 = 0;
             if (B1 > 0) {
                 u32 v1 = rpos0 >> (LOGR - B1);
                 iR0 = p.bitrev_digit ? brev_rt(v1, B1) : v1;
@@ -118,7 +140,7 @@ __device__ __forceinline__ void do_step(u64 *sm, const PassParams &p, const Tabl
                 static_for<0, RAD>([&](auto KAP) {
                     constexpr int q = brev_c(decltype(KAP)::value, B);
                     const u32 row = iR0 + ((u32)KAP << SH);
-                    x[q] = mul(x[q], tc.sm2[padi((row << p.log_w) + c)]);
+                    x[q] = mul(x[q], tc.sm2[padi((row << lw) + c)]);
                 });
                 scaled = true;
             } else if (p.has_outer) {
@@ -147,15 +169,26 @@ __device__ __forceinline__ void do_step(u64 *sm, const PassParams &p, const Tabl
                 static_for<0, RAD>([&](auto K) { x[K] = canon(x[K]); });
             }
         }
-        // natural digit: output kappa -> field value kappa; bit-reversed digit: -> brev(kappa),
-        // i.e. register index q -> field value q.
-        if (p.bitrev_digit) {
+        if (LAST && dout) {
+            // straight to global: natural digit -> output row i_R; bit-reversed digit -> row = position
+            const u64 o0 = tc.out_base + (u64)c * p.out_cs;
+            if (p.bitrev_digit) {
+                static_for<0, RAD>([&](auto Q) { dst[(o0 + (u64)(rpos0 + (u32)Q) * p.out_rs) * es] = x[Q]; });
+            } else {
+                constexpr int SH = B1 + B2;
+                static_for<0, RAD>([&](auto KAP) {
+                    dst[(o0 + (u64)(iR0 + ((u32)KAP << SH)) * p.out_rs) * es] = x[brev_c(decltype(KAP)::value, B)];
+                });
+            }
+        } else if (p.bitrev_digit) {
+            // bit-reversed digit: register index q -> field value q
             static_for<0, RAD>([&](auto Q) { sm[padi(i0 + ((u32)Q << f))] = x[Q]; });
         } else {
+            // natural digit: output kappa -> field value kappa
             static_for<0, RAD>([&](auto KAP) { sm[padi(i0 + ((u32)KAP << f))] = x[brev_c(decltype(KAP)::value, B)]; });
         }
     }
-    __syncthreads();
+    if (!(LAST && dout)) __syncthreads();
 }
 
 template <int LOGR>
@@ -166,12 +199,13 @@ struct Steps {
     static constexpr int C = N == 3 ? LOGR - A - Bb : 0;
 };
 
-template <int LOGR, bool INV>
+template <int LOGR, int LW, bool INV>
 __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, const Tables tb, const u64 *__restrict__ in,
-                                                       u64 *__restrict__ out) {
+                                                          u64 *__restrict__ out) {
     extern __shared__ u64 sm[];
     using S = Steps<LOGR>;
-    const u32 R = 1u << LOGR, W = 1u << p.log_w, T = R << p.log_w;
+    const int lw = LW >= 0 ? LW : (int)p.log_w;
+    const u32 R = 1u << LOGR, W = 1u << lw, T = R << lw;
     const u32 nthreads = blockDim.x, tid = threadIdx.x;
 
     // ---- batch decode
@@ -204,7 +238,6 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, co
 
     // ---- prefetch the last step's multiplier tile (inter-pass twiddles, or the inverse post-scale) into
     //      the second shared buffer with cp.async: it lands while the sub-NTT runs
-    const int lw = p.log_w;
     tc.sm2 = nullptr;
     {
         const u64 *ltab = nullptr;
@@ -227,10 +260,11 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, co
         }
     }
 
-    // ---- global -> shared (coalesced along whichever tile dimension is contiguous); T = 16 * nthreads.
-    //      With a full pre-scale table the coset factor offset^j is applied right here.
+    // lane-contiguous tiles (strided passes) skip the shared-memory staging on the way in / out
+    const bool din = !p.in_r_fast, dout = !p.out_r_fast;
     const u32 es = p.estride;
-    {
+    if (!din) {
+        // ---- global -> shared, coalesced along the transform index; T = 16 * nthreads
         const bool pre = p.has_pre && tc.pre_tab;
         constexpr int CH = 8;   // loads in flight per thread and batch
 #pragma unroll 1
@@ -239,8 +273,7 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, co
 #pragma unroll
             for (int k = 0; k < CH; k++) {
                 const u32 i = (k0 + k) * nthreads + tid;
-                u32 r, c;
-                if (p.in_r_fast) { r = i & (R - 1); c = i >> LOGR; } else { c = i & (W - 1); r = i >> lw; }
+                const u32 r = i & (R - 1), c = i >> LOGR;
                 const u64 e = tc.in_base + (u64)r * p.in_rs + (u64)c * p.in_cs;
                 v[k] = src[e * es];
                 if (pre) tw[k] = __ldg(tc.pre_tab + e);
@@ -248,13 +281,12 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, co
 #pragma unroll
             for (int k = 0; k < CH; k++) {
                 const u32 i = (k0 + k) * nthreads + tid;
-                u32 r, c;
-                if (p.in_r_fast) { r = i & (R - 1); c = i >> LOGR; } else { c = i & (W - 1); r = i >> lw; }
+                const u32 r = i & (R - 1), c = i >> LOGR;
                 sm[padi((r << lw) + c)] = pre ? mul(v[k], tw[k]) : v[k];
             }
         }
+        __syncthreads();
     }
-    __syncthreads();
 
     // ---- CTA-level sub-NTT (the prefetched multiplier tile must be complete and visible to all
     //      threads before the last step)
@@ -266,17 +298,18 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, co
     };
     if constexpr (S::N == 1) {
         tile_ready();
-        do_step<S::A, INV, true, true, 0, 0, LOGR>(sm, p, tb, tc, lw, 0);
+        do_step<S::A, INV, true, true, 0, 0, LOGR, LW>(sm, p, tb, tc, lw, 0, din, dout, src, dst);
     } else if constexpr (S::N == 2) {
-        do_step<S::A, INV, true, false, 0, 0, LOGR>(sm, p, tb, tc, lw + LOGR - S::A, LOGR - S::A);
+        do_step<S::A, INV, true, false, 0, 0, LOGR, LW>(sm, p, tb, tc, lw + LOGR - S::A, LOGR - S::A, din, dout, src, dst);
         tile_ready();
-        do_step<S::Bb, INV, false, true, S::A, 0, LOGR>(sm, p, tb, tc, lw, 0);
+        do_step<S::Bb, INV, false, true, S::A, 0, LOGR, LW>(sm, p, tb, tc, lw, 0, din, dout, src, dst);
     } else {
-        do_step<S::A, INV, true, false, 0, 0, LOGR>(sm, p, tb, tc, lw + LOGR - S::A, LOGR - S::A);
-        do_step<S::Bb, INV, false, false, S::A, 0, LOGR>(sm, p, tb, tc, lw + S::C, S::C);
+        do_step<S::A, INV, true, false, 0, 0, LOGR, LW>(sm, p, tb, tc, lw + LOGR - S::A, LOGR - S::A, din, dout, src, dst);
+        do_step<S::Bb, INV, false, false, S::A, 0, LOGR, LW>(sm, p, tb, tc, lw + S::C, S::C, din, dout, src, dst);
         tile_ready();
-        do_step<S::C, INV, false, true, S::A, S::Bb, LOGR>(sm, p, tb, tc, lw, 0);
+        do_step<S::C, INV, false, true, S::A, S::Bb, LOGR, LW>(sm, p, tb, tc, lw, 0, din, dout, src, dst);
     }
+    if (dout) return;
 
     // ---- shared -> global.  rho = output row (natural digit: i_R, stored at the digit-reversed
     // position; bit-reversed digit: the position itself).
@@ -290,13 +323,12 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, co
 #pragma unroll 4
     for (int k = 0; k < kElemsPerThread; k++) {
         const u32 i = k * nthreads + tid;
-        u32 rho, c;
-        if (p.out_r_fast) { rho = i & (R - 1); c = i >> LOGR; } else { c = i & (W - 1); rho = i >> lw; }
+        const u32 rho = i & (R - 1), c = i >> LOGR;
         dst[(tc.out_base + (u64)rho * p.out_rs + (u64)c * p.out_cs) * es] = sm[padi((pos_of(rho) << lw) + c)];
     }
 }
 
-template <int LOGR>
+template <int LOGR, int LW>
 static void launch_t(const PassParams &p, const Tables &t, bool inverse, const u64 *in, u64 *out, unsigned ntiles,
                      unsigned nbatch, cudaStream_t stream) {
     const unsigned T = 1u << (LOGR + p.log_w);
@@ -305,21 +337,25 @@ static void launch_t(const PassParams &p, const Tables &t, bool inverse, const u
     const size_t smem = (size_t)(T + (T >> 4) + 1) * sizeof(u64) * (two ? 2 : 1);
     static bool attr_set = false;   // per instantiation: allow > 48 KiB of dynamic shared memory
     if (!attr_set) {
-        cudaFuncSetAttribute(ntt_pass_kernel<LOGR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-        cudaFuncSetAttribute(ntt_pass_kernel<LOGR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+        cudaFuncSetAttribute(ntt_pass_kernel<LOGR, LW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+        cudaFuncSetAttribute(ntt_pass_kernel<LOGR, LW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
         attr_set = true;
     }
     dim3 grid(ntiles * nbatch);
     if (inverse)
-        ntt_pass_kernel<LOGR, true><<<grid, threads, smem, stream>>>(p, t, in, out);
+        ntt_pass_kernel<LOGR, LW, true><<<grid, threads, smem, stream>>>(p, t, in, out);
     else
-        ntt_pass_kernel<LOGR, false><<<grid, threads, smem, stream>>>(p, t, in, out);
+        ntt_pass_kernel<LOGR, LW, false><<<grid, threads, smem, stream>>>(p, t, in, out);
 }
 
 void launch_pass(const PassParams &p, const Tables &t, bool inverse, const u64 *in, u64 *out, unsigned ntiles,
                  unsigned nbatch, cudaStream_t stream) {
+    // the shapes large transforms are made of get log2(W) fixed at compile time
+    if (p.log_r == 8 && p.log_w == 4) return launch_t<8, 4>(p, t, inverse, in, out, ntiles, nbatch, stream);
+    if (p.log_r == 7 && p.log_w == 5) return launch_t<7, 5>(p, t, inverse, in, out, ntiles, nbatch, stream);
+    if (p.log_r == 6 && p.log_w == 6) return launch_t<6, 6>(p, t, inverse, in, out, ntiles, nbatch, stream);
     switch (p.log_r) {
-#define MS_CASE(L) case L: launch_t<L>(p, t, inverse, in, out, ntiles, nbatch, stream); break;
+#define MS_CASE(L) case L: launch_t<L, -1>(p, t, inverse, in, out, ntiles, nbatch, stream); break;
         MS_CASE(1) MS_CASE(2) MS_CASE(3) MS_CASE(4) MS_CASE(5) MS_CASE(6)
         MS_CASE(7) MS_CASE(8) MS_CASE(9) MS_CASE(10) MS_CASE(11) MS_CASE(12)
 #undef MS_CASE
