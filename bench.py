@@ -325,12 +325,7 @@ def run_gpu(args):
     host_ce = torch.empty(n, dtype=torch.int64, pin_memory=True)
 
     def e2e_step():
-        if sharded is None:
-            return pipe.run_from_host(host_trace)[0]
-        trace.copy_(host_trace, non_blocking=True)
-        _, r = step()
-        host_ce.copy_(ce_out, non_blocking=True)
-        return r
+        return pipe.run_from_host(host_trace, commit_fn=commit, evaluate_fn=evaluate)[0]
 
     e2e_step()
     barrier()

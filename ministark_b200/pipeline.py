@@ -57,7 +57,7 @@ class TraceCommitPipeline:
         return root
 
     # ---- end to end from host memory
-    def run_from_host(self, host_trace):
+    def run_from_host(self, host_trace, commit_fn=None, evaluate_fn=None):
         """host_trace: pinned (ncols, n) int64 tensor.  Returns (root, pinned host tensor of the composition
         evaluations or None).  H2D of column chunk k+1 overlaps iNTT + LDE of chunk k."""
         assert host_trace.is_pinned() and tuple(host_trace.shape) == (self.ncols, self.n)
@@ -73,8 +73,9 @@ class TraceCommitPipeline:
         for c0, c1, ev in events:
             self.compute.wait_event(ev)
             self.transform(c0, c1)
-        root = self.commit()                          # synchronises: the root is read back
-        self.evaluate()
+        # (multi-GPU: commit_fn / evaluate_fn are the sharded versions, ministark_b200/parallel.py)
+        root = (commit_fn or self.commit)()           # synchronises: the root is read back
+        (evaluate_fn or self.evaluate)()
         if self.ce is not None:
             with torch.cuda.stream(self.compute):
                 self.host_ce.copy_(self.ce, non_blocking=True)
