@@ -173,6 +173,12 @@ int ms_eval_constraints_ptrs(ms_ctx *ctx, const uint32_t *program, unsigned npro
                              int fq_field, unsigned log_m, uint64_t offset_mont, int trace_bitrev, int out_bitrev,
                              void *out);
 
+/* diagnostic, needs no GPU: generate the run-time specialised evaluation kernel for a program (csrc/eval_jit.cu)
+ * and compile it with NVRTC for sm_100a.  0 = ok, 1 = NVRTC not installed (the interpreter kernel is used),
+ * -1 = compile error (log_out receives the NVRTC log) */
+int ms_eval_jit_check(const uint32_t *program, unsigned nprog, const uint64_t *consts, unsigned nconsts, int fq_field,
+                      char *log_out, size_t log_cap);
+
 /* ---- DEEP: out-of-domain evaluations, DeepPolyComposer::get_ood_evals (src/composer.rs:43-86) =
  *      horner_evaluate (src/utils.rs:124-131) of every column at every point, as a parallel reduction ----
  * coeffs: ncols columns of n coefficients of `field`; points: npoints Fq3 elements (3 words each);

@@ -49,6 +49,7 @@ _SIGS = {
     "ms_fri_fold": (ci, [vp, ci, vp, ui, ui, u64, vp, vp]),
     "ms_eval_constraints": (ci, [vp, vp, ui, vp, ui, vp, sz, ui, vp, sz, ui, ci, ui, u64, ci, ci, vp]),
     "ms_eval_constraints_ptrs": (ci, [vp, vp, ui, vp, ui, vp, vp, ui, ci, ui, u64, ci, ci, vp]),
+    "ms_eval_jit_check": (ci, [vp, ui, vp, ui, ci, C.c_char_p, sz]),
     "ms_poly_eval": (ci, [vp, ci, vp, sz, ui, sz, vp, ui, vp]),
     "ms_fill_random": (ci, [vp, vp, sz, u64]),
 }

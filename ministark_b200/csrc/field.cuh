@@ -17,7 +17,9 @@
 //
 // Integer modular arithmetic only: tensor cores are not applicable.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cstdint>
+#endif
 
 namespace gl {
 

@@ -43,3 +43,15 @@ def test_product_never_imports_the_oracle():
                 assert not bad.search(text), f"{f} references the oracle"
     for f in ("include/ministark_b200.h", "include/ministark_gpu.hpp"):
         assert not bad.search(open(os.path.join(root, f)).read())
+
+
+def test_specialised_eval_kernel_compiles_for_sm100a():
+    """csrc/eval_jit.cu: the evaluator generated for a program compiles with NVRTC (no GPU needed)."""
+    from ministark_b200 import expr as E
+    lib = _lib.load()
+    ex = (E.Trace(0, 1) - E.Trace(0, 0) * E.Trace(1, 0)) / (E.X() ** 8 - 1) * (E.Challenge(0) + E.Hint(0)) + E.Trace(2, -1) ** 3
+    for fq in (1, 3):
+        prog = E.compile_program(ex, 2 if fq == 3 else 3, [(3, 4, 5)], [(6, 7, 8)], log_ce=6)
+        log = ctypes.create_string_buffer(8192)
+        rc = lib.ms_eval_jit_check(prog.code.ctypes.data, len(prog), prog.consts.ctypes.data, prog.consts.shape[0], fq, log, 8192)
+        assert rc in (0, 1), log.value.decode()[:2000]      # 1 = NVRTC not installed: interpreter kernel is used
