@@ -132,6 +132,8 @@ int ntt_get_plan(ms_ctx *c, const NttJob &job, std::shared_ptr<NttPlanDev> *out)
             p.dims[1] = msntt::Dim{(u32)(N / (R * Rprev)), 0, R * Rprev, R * Rprev, 0};
         }
         p.log_w = (u32)ilog2(W);
+        for (u32 dd = 0; dd < p.ndims; dd++) p.dims[dd].log_ext = (u32)ilog2(p.dims[dd].ext);
+        p.log_ncos = (u32)ilog2(P->ncos);
         p.has_pre = (k == 0 && has_pre) ? 1 : 0;
         p.has_post = (k == m - 1 && has_post) ? 1 : 0;
         P->passes.push_back(p);
@@ -278,7 +280,8 @@ int ntt_run(ms_ctx *c, NttPlanDev &P, const u64 *in, size_t in_cs, u64 *out, siz
     for (unsigned t : P.ntiles) max_tiles = std::max(max_tiles, t);
     // 1-D grid of ntiles * nbatch blocks (naive path: grid.y = columns * lanes)
     unsigned max_cols = P.naive ? 65535u / P.lanes
-                                : (unsigned)std::max<u64>(1, (0x7FFFFFFFull / max_tiles) / (P.lanes * P.ncos));
+                                : (unsigned)std::max<u64>(1, 0x7FFFFFFFull / (P.lanes * P.ncos));
+    (void)max_tiles;
     const int m = (int)P.passes.size();
     const bool need_tmp = P.naive ? (in == out) : (!lde && m >= 2);
     if (need_tmp) max_cols = (unsigned)std::max<size_t>(1, std::min<size_t>(max_cols, tmp_budget / (col_words * 8)));

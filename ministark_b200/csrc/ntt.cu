@@ -77,6 +77,9 @@ __device__ __forceinline__ void do_step(u64 *sm, const PassParams &p, const Tabl
     const u32 nthreads = blockDim.x, tid = threadIdx.x;
     const u32 wmask = (1u << lw) - 1;
     const u32 es = p.estride;
+    // compile-time tile geometry (LW >= 0) is only dispatched when every in-column word offset fits 32 bits
+    // (launch_pass checks): offsets then cost one IMAD.WIDE on the FMA pipe instead of 64-bit ALU chains
+    using idx_t = typename std::conditional<(LW >= 0), u32, u64>::type;
 #pragma unroll 1
     for (int gi = 0; gi < G; gi++) {
         const u32 g = gi * nthreads + tid;
@@ -86,16 +89,19 @@ __device__ __forceinline__ void do_step(u64 *sm, const PassParams &p, const Tabl
         if (FIRST && din) {
             // rows rpos0 + (K << (f - lw)), lane c: 16 coalesced global loads (2 x 128 B per warp each)
             const u64 e0 = tc.in_base + (u64)rpos0 * p.in_rs + (u64)c * p.in_cs;
-            const u64 stj = p.in_rs << (f - lw);
+            const idx_t stj = (idx_t)(p.in_rs << (f - lw));
+            const u64 *sp = src + e0 * es;
+            const idx_t stw = stj * (idx_t)es;
             if (p.has_pre && tc.pre_tab) {
+                const u64 *tp = tc.pre_tab + e0;
                 u64 tw[RAD];
                 static_for<0, RAD>([&](auto K) {
-                    x[K] = src[(e0 + (u64)K * stj) * es];
-                    tw[K] = __ldg(tc.pre_tab + e0 + (u64)K * stj);
+                    x[K] = sp[(idx_t)K * stw];
+                    tw[K] = __ldg(tp + (idx_t)K * stj);
                 });
                 static_for<0, RAD>([&](auto K) { x[K] = mul(x[K], tw[K]); });
             } else {
-                static_for<0, RAD>([&](auto K) { x[K] = src[(e0 + (u64)K * stj) * es]; });
+                static_for<0, RAD>([&](auto K) { x[K] = sp[(idx_t)K * stw]; });
             }
         } else {
             static_for<0, RAD>([&](auto K) { x[K] = sm[padi(i0 + ((u32)K << f))]; });
@@ -171,14 +177,14 @@ __device__ __forceinline__ void do_step(u64 *sm, const PassParams &p, const Tabl
         }
         if (LAST && dout) {
             // straight to global: natural digit -> output row i_R; bit-reversed digit -> row = position
-            const u64 o0 = tc.out_base + (u64)c * p.out_cs;
+            const idx_t ors = (idx_t)p.out_rs * (idx_t)es;
             if (p.bitrev_digit) {
-                static_for<0, RAD>([&](auto Q) { dst[(o0 + (u64)(rpos0 + (u32)Q) * p.out_rs) * es] = x[Q]; });
+                u64 *dp = dst + (tc.out_base + (u64)c * p.out_cs + (u64)rpos0 * p.out_rs) * es;
+                static_for<0, RAD>([&](auto Q) { dp[(idx_t)Q * ors] = x[Q]; });
             } else {
                 constexpr int SH = B1 + B2;
-                static_for<0, RAD>([&](auto KAP) {
-                    dst[(o0 + (u64)(iR0 + ((u32)KAP << SH)) * p.out_rs) * es] = x[brev_c(decltype(KAP)::value, B)];
-                });
+                u64 *dp = dst + (tc.out_base + (u64)c * p.out_cs + (u64)iR0 * p.out_rs) * es;
+                static_for<0, RAD>([&](auto KAP) { dp[(idx_t)((u32)KAP << SH) * ors] = x[brev_c(decltype(KAP)::value, B)]; });
             }
         } else if (p.bitrev_digit) {
             // bit-reversed digit: register index q -> field value q
@@ -211,10 +217,11 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, co
     // ---- batch decode
     // linear block id = tile * nbatch + batch: the batch (column / coset / lane) varies fastest, so the
     // CTAs that share a twiddle-table tile run together and the tables are served from L2
-    const u32 b = blockIdx.x % p.nbatch;
-    const u32 lane = b % p.lanes;
-    const u32 cos = (b / p.lanes) % p.ncos;
-    const u32 col = b / (p.lanes * p.ncos);
+    // grid = (batch, tiles lo, tiles hi): blocks are dispatched x-fastest
+    u32 b = blockIdx.x, lane = 0;
+    if (p.lanes == 3) { lane = b % 3; b /= 3; }
+    const u32 cos = b & (p.ncos - 1);
+    const u32 col = b >> p.log_ncos;
     const u64 *src = in + (u64)col * p.in_col_stride + (u64)cos * p.in_cos_stride + lane;
     u64 *dst = out + (u64)col * p.out_col_stride + (u64)cos * p.out_cos_stride + lane;
 
@@ -222,10 +229,10 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, co
     TileCtx tc;
     tc.in_base = tc.out_base = tc.low_base = 0;
     {
-        u32 t = blockIdx.x / p.nbatch;
+        u32 t = blockIdx.y + blockIdx.z * gridDim.y;
         for (u32 d = 0; d < p.ndims; d++) {
-            u32 idx = t % p.dims[d].ext;
-            t /= p.dims[d].ext;
+            const u32 idx = t & (p.dims[d].ext - 1);
+            t >>= p.dims[d].log_ext;
             tc.in_base += (u64)idx * p.dims[d].in_str;
             tc.out_base += (u64)idx * p.dims[d].out_str;
             tc.low_base += (u64)idx * p.dims[d].low_str;
@@ -248,13 +255,15 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, co
             ltab = p.post_tab + tc.out_base; lrs = p.out_rs; lcs = p.out_cs;
         }
         if (ltab) {
+            using idx_t = typename std::conditional<(LW >= 0), u32, u64>::type;
             u64 *sm2 = sm + (T + (T >> 4) + 1);
             tc.sm2 = sm2;
+            const idx_t lrs_i = (idx_t)lrs, lcs_i = (idx_t)lcs;
 #pragma unroll
             for (int k = 0; k < kElemsPerThread; k++) {
                 const u32 i = k * nthreads + tid;
                 const u32 c = i & (W - 1), r = i >> lw;
-                cp_async8(sm2 + padi(i), ltab + (u64)r * lrs + (u64)c * lcs);
+                cp_async8(sm2 + padi(i), ltab + ((idx_t)r * lrs_i + (idx_t)c * lcs_i));
             }
             cp_async_commit();
         }
@@ -270,13 +279,16 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, co
 #pragma unroll 1
         for (int k0 = 0; k0 < kElemsPerThread; k0 += CH) {
             u64 v[CH], tw[CH];
+            using idx_t = typename std::conditional<(LW >= 0), u32, u64>::type;
+            const u64 *sp = src + tc.in_base * es;
+            const u64 *tp = pre ? tc.pre_tab + tc.in_base : nullptr;
 #pragma unroll
             for (int k = 0; k < CH; k++) {
                 const u32 i = (k0 + k) * nthreads + tid;
                 const u32 r = i & (R - 1), c = i >> LOGR;
-                const u64 e = tc.in_base + (u64)r * p.in_rs + (u64)c * p.in_cs;
-                v[k] = src[e * es];
-                if (pre) tw[k] = __ldg(tc.pre_tab + e);
+                const idx_t e = (idx_t)r * (idx_t)p.in_rs + (idx_t)c * (idx_t)p.in_cs;
+                v[k] = sp[e * (idx_t)es];
+                if (pre) tw[k] = __ldg(tp + e);
             }
 #pragma unroll
             for (int k = 0; k < CH; k++) {
@@ -320,11 +332,15 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, co
         u32 k1 = rho & ((1u << S::A) - 1), k2 = (rho >> S::A) & ((1u << S::Bb) - 1), k3 = rho >> (S::A + S::Bb);
         return (k1 << (LOGR - S::A)) | (k2 << S::C) | k3;
     };
+    {
+        using idx_t = typename std::conditional<(LW >= 0), u32, u64>::type;
+        u64 *dp = dst + tc.out_base * es;
 #pragma unroll 4
-    for (int k = 0; k < kElemsPerThread; k++) {
-        const u32 i = k * nthreads + tid;
-        const u32 rho = i & (R - 1), c = i >> LOGR;
-        dst[(tc.out_base + (u64)rho * p.out_rs + (u64)c * p.out_cs) * es] = sm[padi((pos_of(rho) << lw) + c)];
+        for (int k = 0; k < kElemsPerThread; k++) {
+            const u32 i = k * nthreads + tid;
+            const u32 rho = i & (R - 1), c = i >> LOGR;
+            dp[((idx_t)rho * (idx_t)p.out_rs + (idx_t)c * (idx_t)p.out_cs) * (idx_t)es] = sm[padi((pos_of(rho) << lw) + c)];
+        }
     }
 }
 
@@ -341,7 +357,8 @@ static void launch_t(const PassParams &p, const Tables &t, bool inverse, const u
         cudaFuncSetAttribute(ntt_pass_kernel<LOGR, LW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
         attr_set = true;
     }
-    dim3 grid(ntiles * nbatch);
+    const unsigned ty = ntiles < 32768u ? ntiles : 32768u;   // ntiles is a power of two
+    dim3 grid(nbatch, ty, ntiles / ty);
     if (inverse)
         ntt_pass_kernel<LOGR, LW, true><<<grid, threads, smem, stream>>>(p, t, in, out);
     else
@@ -351,9 +368,13 @@ static void launch_t(const PassParams &p, const Tables &t, bool inverse, const u
 void launch_pass(const PassParams &p, const Tables &t, bool inverse, const u64 *in, u64 *out, unsigned ntiles,
                  unsigned nbatch, cudaStream_t stream) {
     // the shapes large transforms are made of get log2(W) fixed at compile time
+    // ... provided every word offset inside a column (and inside the twiddle / scale tables) fits in 32 bits
+    const bool small = ((p.n_mask + 1) * (u64)p.estride) <= (1ull << 31);
+    if (!small) goto generic;
     if (p.log_r == 8 && p.log_w == 4) return launch_t<8, 4>(p, t, inverse, in, out, ntiles, nbatch, stream);
     if (p.log_r == 7 && p.log_w == 5) return launch_t<7, 5>(p, t, inverse, in, out, ntiles, nbatch, stream);
     if (p.log_r == 6 && p.log_w == 6) return launch_t<6, 6>(p, t, inverse, in, out, ntiles, nbatch, stream);
+generic:
     switch (p.log_r) {
 #define MS_CASE(L) case L: launch_t<L, -1>(p, t, inverse, in, out, ntiles, nbatch, stream); break;
         MS_CASE(1) MS_CASE(2) MS_CASE(3) MS_CASE(4) MS_CASE(5) MS_CASE(6)

@@ -17,8 +17,8 @@ constexpr int kTileLog = 12;          // a CTA tile holds at most 4096 elements 
 constexpr int kElemsPerThread = 16;   // radix-16 register butterflies
 
 struct Dim {
-    u32 ext;      // number of values enumerated by the tile id
-    u32 _pad;
+    u32 ext;      // number of values enumerated by the tile id (a power of two)
+    u32 log_ext;
     u64 in_str;   // element strides
     u64 out_str;
     u64 low_str;  // contribution to the "lower index" of the outer twiddle
@@ -46,7 +46,8 @@ struct PassParams {
     u64 in_col_stride, out_col_stride;   // words
     u64 in_cos_stride, out_cos_stride;   // words
     u32 estride;                         // words per element (1 Fp, 3 Fq3)
-    u32 nbatch;                          // columns * coset blocks * lanes (linear block id % nbatch)
+    u32 nbatch;                          // columns * coset blocks * lanes = gridDim.x (batch varies fastest)
+    u32 log_ncos;
     // optional full tables (replace the per-thread geometric progressions: one multiplication per
     // element instead of two; shared by every column / coset of the batch, so they stay in L2)
     const u64 *outer_tab;                // [i_R * outer_S + lower] = omega_{N_k}^(i_R * lower)
