@@ -21,13 +21,26 @@ using msntt::brev_c;
 using msntt::IC;
 using msntt::static_for;
 
+// rows are FF*LANES consecutive words; a CTA first copies its block of rows into shared memory with fully
+// coalesced loads (row pitch padded by one word: conflict-free row reads), then each thread folds one row
 template <int LOGFF, int LANES>
 __global__ void __launch_bounds__(128) fri_fold_kernel(const u64 *__restrict__ evals, u64 *__restrict__ out, size_t m,
-                                                        unsigned log_m, u64 offset_inv, u64 g_inv, u64 a0, u64 a1, u64 a2) {
+                                                        unsigned log_m, u64 offset_inv, const u64 *__restrict__ tw_lo, const u64 *__restrict__ tw_hi,
+                                                        unsigned hi_len, u64 n_mask, u64 a0, u64 a1, u64 a2) {
     constexpr int FF = 1 << LOGFF;
-    const size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    constexpr int RW = FF * LANES, PITCH = RW + 1;
+    extern __shared__ u64 rows_sm[];
+    const size_t k0 = blockIdx.x * (size_t)blockDim.x;
+    const size_t k = k0 + threadIdx.x;
+    {
+        const size_t rows_here = (m - k0) < (size_t)blockDim.x ? (m - k0) : (size_t)blockDim.x;
+        const size_t words = rows_here * RW;
+        const u64 *blk = evals + k0 * RW;
+        for (size_t w = threadIdx.x; w < words; w += blockDim.x) rows_sm[(w / RW) * PITCH + (w % RW)] = blk[w];
+    }
+    __syncthreads();
     if (k >= m) return;
-    const u64 *src = evals + k * FF * LANES;
+    const u64 *src = rows_sm + (size_t)threadIdx.x * PITCH;
     u64 D[LANES][FF];
 #pragma unroll
     for (int l = 0; l < LANES; l++) {
@@ -37,9 +50,12 @@ __global__ void __launch_bounds__(128) fri_fold_kernel(const u64 *__restrict__ e
         msntt::dft_regs<LOGFF, true>(x);
         static_for<0, FF>([&](auto J) { D[l][decltype(J)::value] = gl::canon(x[brev_c(decltype(J)::value, LOGFF)]); });
     }
-    // 1 / x_k = offset^-1 * g^-bitrev_m(k)
+    // 1 / x_k = offset^-1 * g^-bitrev_m(k) = offset^-1 * g^(n - bitrev_m(k)), from the two-level table of g_n^e
     const u64 e = log_m ? (__brevll((u64)k) >> (64 - log_m)) : 0;
-    const u64 xinv = gl::mul(offset_inv, gl::pow(g_inv, e));
+    const u64 ne = (n_mask + 1 - e) & n_mask;
+    u64 gpow = tw_lo[ne & 4095];
+    if (hi_len > 1) gpow = gl::mul(tw_hi[ne >> 12], gpow);
+    const u64 xinv = gl::mul(offset_inv, gpow);
     if constexpr (LANES == 1) {
         const u64 beta = gl::mul(a0, xinv);
         u64 acc = D[0][FF - 1];
@@ -76,11 +92,15 @@ extern "C" int ms_fri_fold(ms_ctx *c, int field, const void *evals, unsigned log
     if (in.rc) return in.rc;
     Staged o(c, out, m * field * 8, false, true);
     if (o.rc) return o.rc;
-    u64 g = gl::to_mont(1753635133440165772ULL);
-    for (unsigned i = log_n; i < 32; i++) g = gl::sqr(g);
-    const u64 g_inv = gl::inv(g), off_inv = gl::inv(offset_mont);
-    const unsigned threads = 128, blocks = (unsigned)((m + threads - 1) / threads), log_m = log_n - log_ff;
-#define MS_FF(L, F) fri_fold_kernel<L, F><<<blocks, threads, 0, c->stream>>>(in.as<u64>(), o.as<u64>(), m, log_m, off_inv, g_inv, a[0], a[1], a[2])
+    const u64 off_inv = gl::inv(offset_mont);
+    const u64 *tw_lo, *tw_hi;
+    u32 hi_len;
+    if (int trc = ntt_plan_tables(c, log_n, &tw_lo, &tw_hi, &hi_len)) return trc;
+    const u64 n_mask = (u64)n - 1;
+    const unsigned threads = (field == 3 && log_ff == 4) ? 64 : 128, blocks = (unsigned)((m + threads - 1) / threads),
+                   log_m = log_n - log_ff;
+    const size_t smem = (size_t)threads * (((size_t)field << log_ff) + 1) * 8;
+#define MS_FF(L, F) fri_fold_kernel<L, F><<<blocks, threads, smem, c->stream>>>(in.as<u64>(), o.as<u64>(), m, log_m, off_inv, tw_lo, tw_hi, hi_len, n_mask, a[0], a[1], a[2])
     if (field == 1) {
         switch (log_ff) { case 1: MS_FF(1, 1); break; case 2: MS_FF(2, 1); break; case 3: MS_FF(3, 1); break; default: MS_FF(4, 1); }
     } else {
