@@ -52,6 +52,7 @@ bool is_device_ptr(const void *p) {
 
 Staged::Staged(ms_ctx *c, const void *p, size_t nbytes, bool copy_in, bool copy_out_)
     : ctx(c), user(const_cast<void *>(p)), dev(nullptr), bytes(nbytes), staged(false), copy_out(copy_out_), rc(MS_OK) {
+    cudaSetDevice(c->device);   // every entry point builds a Staged first: the context's device becomes current
     if (p == nullptr || nbytes == 0 || is_device_ptr(p)) {
         dev = user;
         return;

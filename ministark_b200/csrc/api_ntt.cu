@@ -366,6 +366,7 @@ int ms_ntt_plan_create(ms_ctx *c, int field, unsigned log_n, int direction, uint
     if (log_n > 32) return fail(c, MS_ERR_INVALID, "log_n %u out of range [0, 32]", log_n);
     if (direction != MS_NTT_FORWARD && direction != MS_NTT_INVERSE) return fail(c, MS_ERR_INVALID, "bad direction");
     if (offset_mont >= gl::P || offset_mont == 0) return fail(c, MS_ERR_INVALID, "offset must be a non-zero canonical word");
+    cudaSetDevice(c->device);
     NttJob job{field, log_n, direction == MS_NTT_INVERSE, false, 0, offset_mont};
     auto *pl = new ms_ntt_plan();
     pl->ctx = c;
@@ -387,6 +388,7 @@ int ms_ntt_encode(ms_ntt_plan *pl, void *column) {
 int ms_ntt_execute(ms_ntt_plan *pl) {
     if (!pl) return MS_ERR_INVALID;
     ms_ctx *c = pl->ctx;
+    cudaSetDevice(c->device);
     NttPlanDev &P = *pl->plan;
     const size_t col_words = (size_t)P.N * P.estride;
     std::vector<void *> host_cols, dev_cols;

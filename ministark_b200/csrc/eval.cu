@@ -263,6 +263,7 @@ extern "C" int ms_eval_constraints_ptrs(ms_ctx *c, const uint32_t *program, unsi
     if (fq_field != MS_FIELD_FP && fq_field != MS_FIELD_FQ3) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: bad Fq field id");
     if (log_m > 32) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: domain too large");
     if (offset_mont >= gl::P || offset_mont == 0) return fail(c, MS_ERR_INVALID, "offset must be a non-zero canonical word");
+    cudaSetDevice(c->device);
     std::vector<const u64 *> cols;
     std::vector<int> isq;
     for (unsigned i = 0; i < ncols; i++) {

@@ -351,11 +351,14 @@ static void launch_t(const PassParams &p, const Tables &t, bool inverse, const u
     const unsigned threads = T / kElemsPerThread;
     const bool two = (p.has_outer && p.outer_tab) || (p.has_post && p.post_tab);
     const size_t smem = (size_t)(T + (T >> 4) + 1) * sizeof(u64) * (two ? 2 : 1);
-    static bool attr_set = false;   // per instantiation: allow > 48 KiB of dynamic shared memory
-    if (!attr_set) {
+    // per instantiation and per device: allow > 48 KiB of dynamic shared memory
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         cudaFuncSetAttribute(ntt_pass_kernel<LOGR, LW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
         cudaFuncSetAttribute(ntt_pass_kernel<LOGR, LW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     const unsigned ty = ntiles < 32768u ? ntiles : 32768u;   // ntiles is a power of two
     dim3 grid(nbatch, ty, ntiles / ty);
