@@ -39,6 +39,8 @@ __device__ __forceinline__ u32 small_sigma1(u32 w) { return rotr(w, 17) ^ rotr(w
 // K[i] + W[i] of the constant second block of a 64-byte message (0x80, zeros, bit length 512): the
 // Merkle node hash needs no message schedule for it.
 __constant__ u32 c_KW_pad64[64];
+// same for the padding block that follows a leaf row whose length is a multiple of 64 bytes (set per launch)
+__constant__ u32 c_KW_padrow[64];
 
 struct Sha {
     u32 h[8];
@@ -62,12 +64,13 @@ struct Sha {
         h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
     }
     // compression of the constant padding block that follows a 64-byte message
-    __device__ __forceinline__ void compress_pad64() {
+    __device__ __forceinline__ void compress_pad64() { compress_const(c_KW_pad64); }
+    __device__ __forceinline__ void compress_const(const u32 (&kw)[64]) {
         u32 a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
 #pragma unroll
         for (int i = 0; i < 64; i++) {
             u32 ch = (e & f) ^ (~e & g);
-            u32 t1 = hh + big_sigma1(e) + ch + c_KW_pad64[i];
+            u32 t1 = hh + big_sigma1(e) + ch + kw[i];
             u32 mj = (a & b) ^ (a & c) ^ (b & c);
             u32 t2 = big_sigma0(a) + mj;
             hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
@@ -87,7 +90,7 @@ struct Sha {
 // cols[(t / lanes) * col_stride_words + i * lanes + t % lanes].
 __global__ void __launch_bounds__(128) hash_rows_kernel(const u64 *__restrict__ cols, size_t col_stride_words,
                                                          unsigned lanes, unsigned words_per_row, size_t nrows,
-                                                         u32 *__restrict__ digests) {
+                                                         u32 *__restrict__ digests, int const_pad) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= nrows) return;
     Sha s;
@@ -97,7 +100,8 @@ __global__ void __launch_bounds__(128) hash_rows_kernel(const u64 *__restrict__ 
     const u64 bitlen = (u64)words_per_row * 64;
     const u64 *row = cols + i * lanes;
     unsigned t = 0, cidx = 0, l = 0;  // running word index -> (column, lane)
-    for (unsigned blk = 0; blk * 16 < total32; blk++) {
+    const unsigned data_blocks = const_pad ? msg_words32 / 16 : total32 / 16;   // const_pad: the last block is pure padding
+    for (unsigned blk = 0; blk < data_blocks; blk++) {
         u32 w[16];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
@@ -118,6 +122,7 @@ __global__ void __launch_bounds__(128) hash_rows_kernel(const u64 *__restrict__ 
         }
         s.compress(w);
     }
+    if (const_pad) s.compress_const(c_KW_padrow);
     s.store(digests + i * 8);
 }
 
@@ -140,23 +145,53 @@ __global__ void __launch_bounds__(128) merkle_level_kernel(const u32 *__restrict
     s.store(dst + k * 8);
 }
 
+static int upload_row_pad_schedule(ms_ctx *c, unsigned row_words);
 static int hash_rows_dev(ms_ctx *c, int field, const u64 *cols, size_t col_stride_elems, unsigned ncols, size_t nrows,
                          u32 *digests) {
     if (nrows == 0) return MS_OK;
     const unsigned threads = 128;
+    const int const_pad = upload_row_pad_schedule(c, ncols * field);
     hash_rows_kernel<<<(unsigned)((nrows + threads - 1) / threads), threads, 0, c->stream>>>(
-        cols, col_stride_elems * field, (unsigned)field, ncols * field, nrows, digests);
+        cols, col_stride_elems * field, (unsigned)field, ncols * field, nrows, digests, const_pad);
     c->launches++;
     MS_CHECK_LAUNCH(c);
     return MS_OK;
 }
 
 static u32 h_rotr(u32 x, int r) { return (x >> r) | (x << (32 - r)); }
+// K[i] + W[i] for the block {0x80000000, 0, ..., bitlen_hi, bitlen_lo}
+static void pad_schedule(unsigned long long bitlen, u32 kw[64]);
 static int upload_pad_schedule(ms_ctx *c) {
     static bool done[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 64 && done[dev]) return MS_OK;
+    if (dev >= 0 && dev < 64 && done[dev]) return MS_OK;
+    u32 kw[64];
+    pad_schedule(512, kw);
+    MS_CUDA(c, cudaMemcpyToSymbol(c_KW_pad64, kw, sizeof kw));
+    if (dev >= 0 && dev < 64) done[dev] = true;
+    return MS_OK;
+}
+// leaf rows: returns 1 (and uploads the schedule) if row_words*8 bytes is a multiple of 64, else 0
+static int upload_row_pad_schedule(ms_ctx *c, unsigned row_words) {
+    if (row_words % 8) return 0;
+    static unsigned long long last[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bitlen = (unsigned long long)row_words * 64;
+    if (dev >= 0 && dev < 64 && last[dev] == bitlen) return 1;
+    u32 kw[64];
+    pad_schedule(bitlen, kw);
+    // stream-ordered so that a launch still in flight with another row length is not disturbed
+    if (cudaMemcpyToSymbolAsync(c_KW_padrow, kw, sizeof kw, 0, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    cudaStreamSynchronize(c->stream);   // kw is a stack buffer
+    if (dev >= 0 && dev < 64) last[dev] = bitlen;
+    return 1;
+}
+static void pad_schedule(unsigned long long bitlen, u32 kw[64]) {
     static const u32 K[64] = {
         0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
         0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
@@ -166,18 +201,16 @@ static int upload_pad_schedule(ms_ctx *c) {
         0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
         0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
         0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
-    u32 w[64] = {0}, kw[64];
+    u32 w[64] = {0};
     w[0] = 0x80000000u;
-    w[15] = 512;
+    w[14] = (u32)(bitlen >> 32);
+    w[15] = (u32)bitlen;
     for (int i = 16; i < 64; i++) {
         u32 s0 = h_rotr(w[i - 15], 7) ^ h_rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
         u32 s1 = h_rotr(w[i - 2], 17) ^ h_rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
         w[i] = w[i - 16] + s0 + w[i - 7] + s1;
     }
     for (int i = 0; i < 64; i++) kw[i] = K[i] + w[i];
-    MS_CUDA(c, cudaMemcpyToSymbol(c_KW_pad64, kw, sizeof kw));
-    if (dev < 64) done[dev] = true;
-    return MS_OK;
 }
 
 static int merkle_nodes_dev(ms_ctx *c, const u32 *leaves, size_t n, u32 *nodes) {
@@ -285,8 +318,9 @@ int ms_merkle_commit_rows_sha256(ms_ctx *c, const void *rows, unsigned row_words
     else if ((rc = scratch_get(c, 3, nrows * 32, &nd))) return rc;
     // one "column" whose element is the whole row: word t of row i at base + i*row_words + t
     const unsigned threads = 128;
+    const int const_pad = upload_row_pad_schedule(c, row_words);
     hash_rows_kernel<<<(unsigned)((nrows + threads - 1) / threads), threads, 0, c->stream>>>(in.as<u64>(), 0, row_words, row_words,
-                                                                                              nrows, (u32 *)lv);
+                                                                                              nrows, (u32 *)lv, const_pad);
     c->launches++;
     MS_CHECK_LAUNCH(c);
     if ((rc = merkle_nodes_dev(c, (const u32 *)lv, nrows, (u32 *)nd))) return rc;
