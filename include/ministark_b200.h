@@ -135,6 +135,11 @@ int ms_merkle_commit_sha256(ms_ctx *ctx, int field, const void *cols, size_t col
 int ms_merkle_commit_rows_sha256(ms_ctx *ctx, const void *rows, unsigned row_words, size_t nrows, void *leaves,
                                  void *nodes, void *root);
 
+/* ---- proof of work: PublicCoin::grind_proof_of_work (src/random.rs:48-55,129-132; src/channel.rs:76-93) ----
+ * smallest nonce >= 1 with leading_zeros(SHA-256(seed[32] || nonce as 8 big-endian bytes)) >= bits
+ * (deterministic, unlike the reference's rayon find_any) */
+int ms_pow_grind_sha256(ms_ctx *ctx, const uint8_t *seed, unsigned bits, uint64_t *nonce_out);
+
 /* ---- matrix plumbing ----
  * Matrix::from_arrays / from_rows (src/matrix.rs:33-64) and the composition split (src/prover.rs:113-120):
  * n rows of k elements (row-major) -> k columns of n elements */

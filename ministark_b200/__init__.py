@@ -168,6 +168,13 @@ class Context:
                                                        root.ctypes.data))
         return root.tobytes()
 
+    def pow_grind(self, seed, bits):
+        """smallest nonce >= 1 with leading_zeros(SHA-256(seed || nonce_be8)) >= bits (src/random.rs:48-55)"""
+        sd = (C.c_uint8 * 32).from_buffer_copy(bytes(seed))
+        out = C.c_uint64()
+        self._ck(self.lib.ms_pow_grind_sha256(self.h, sd, bits, C.byref(out)))
+        return int(out.value)
+
     def matrix_from_rows(self, rows, cols, field, n, k, col_stride=None):
         self._ck(self.lib.ms_matrix_from_rows(self.h, field, _ptr(rows), n, k, _ptr(cols), n if col_stride is None else col_stride))
 

@@ -44,6 +44,7 @@ _SIGS = {
     "ms_merkle_nodes_sha256": (ci, [vp, vp, sz, vp]),
     "ms_merkle_commit_sha256": (ci, [vp, ci, vp, sz, ui, sz, vp, vp, vp]),
     "ms_merkle_commit_rows_sha256": (ci, [vp, vp, ui, sz, vp, vp, vp]),
+    "ms_pow_grind_sha256": (ci, [vp, vp, ui, C.POINTER(u64)]),
     "ms_matrix_from_rows": (ci, [vp, ci, vp, sz, ui, vp, sz]),
     "ms_gather_rows": (ci, [vp, ci, vp, sz, ui, sz, vp, ui, vp]),
     "ms_fri_fold": (ci, [vp, ci, vp, ui, ui, u64, vp, vp]),

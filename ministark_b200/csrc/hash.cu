@@ -145,6 +145,26 @@ __global__ void __launch_bounds__(128) merkle_level_kernel(const u32 *__restrict
     s.store(dst + k * 8);
 }
 
+// Proof-of-work grinding (PublicCoin::grind_proof_of_work, src/random.rs:48-55,129-132; called from
+// ProverChannel::grind_fri_commitments, src/channel.rs:76-93): find a nonce with
+// leading_zeros(SHA-256(seed || nonce.to_be_bytes())) >= bits.  The reference's parallel search returns ANY
+// such nonce (rayon find_any), which makes proof bytes non-deterministic; here every batch of candidates is
+// reduced with atomicMin, so the SMALLEST nonce >= 1 is returned — the value the reference's serial branch finds.
+__global__ void __launch_bounds__(128) pow_grind_kernel(uint4 seed_lo, uint4 seed_hi, unsigned bits, u64 base, u64 count,
+                                                         unsigned long long *best) {
+    const u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    const u64 nonce = base + idx;
+    Sha s;
+    s.init();
+    u32 w[16] = {seed_lo.x, seed_lo.y, seed_lo.z, seed_lo.w, seed_hi.x, seed_hi.y, seed_hi.z, seed_hi.w,
+                 (u32)(nonce >> 32), (u32)nonce, 0x80000000u, 0, 0, 0, 0, 320};
+    s.compress(w);
+    unsigned lz = __clz(s.h[0]);
+    if (s.h[0] == 0) { lz = 32 + __clz(s.h[1]); if (s.h[1] == 0) lz = 64 + __clz(s.h[2]); }
+    if (lz >= bits) atomicMin(best, (unsigned long long)nonce);
+}
+
 static int upload_row_pad_schedule(ms_ctx *c, unsigned row_words);
 static int hash_rows_dev(ms_ctx *c, int field, const u64 *cols, size_t col_stride_elems, unsigned ncols, size_t nrows,
                          u32 *digests) {
@@ -329,6 +349,37 @@ int ms_merkle_commit_rows_sha256(ms_ctx *c, const void *rows, unsigned row_words
     if ((rc = in.finish())) return rc;
     if ((rc = lout.finish())) return rc;
     return nout.finish();
+}
+
+
+int ms_pow_grind_sha256(ms_ctx *c, const uint8_t *seed, unsigned bits, uint64_t *nonce_out) {
+    if (!c || !seed || !nonce_out) return MS_ERR_INVALID;
+    if (bits > 64) return fail(c, MS_ERR_INVALID, "ms_pow_grind_sha256: at most 64 bits supported");
+    cudaSetDevice(c->device);
+    u32 sw[8];
+    for (int i = 0; i < 8; i++)
+        sw[i] = ((u32)seed[4 * i] << 24) | ((u32)seed[4 * i + 1] << 16) | ((u32)seed[4 * i + 2] << 8) | seed[4 * i + 3];
+    void *best;
+    int rc = scratch_get(c, 3, 64, &best);
+    if (rc) return rc;
+    const unsigned long long none = ~0ull;
+    const u64 batch = 1ull << 24;
+    for (u64 base = 1;; base += batch) {   // (1..u64::MAX), src/random.rs:50
+        MS_CUDA(c, cudaMemcpyAsync(best, &none, 8, cudaMemcpyHostToDevice, c->stream));
+        pow_grind_kernel<<<(unsigned)(batch / 128), 128, 0, c->stream>>>(make_uint4(sw[0], sw[1], sw[2], sw[3]),
+                                                                         make_uint4(sw[4], sw[5], sw[6], sw[7]), bits, base, batch,
+                                                                         (unsigned long long *)best);
+        c->launches++;
+        MS_CHECK_LAUNCH(c);
+        unsigned long long got = none;
+        MS_CUDA(c, cudaMemcpyAsync(&got, best, 8, cudaMemcpyDeviceToHost, c->stream));
+        MS_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (got != none) {
+            *nonce_out = got;
+            return MS_OK;
+        }
+        if (base > (~0ull) - 2 * batch) return fail(c, MS_ERR_INVALID, "nonce not found");   // .expect("nonce not found")
+    }
 }
 
 }  // extern "C"

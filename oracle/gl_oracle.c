@@ -664,6 +664,26 @@ void orc_degree_adjust(u64 *coeffs, size_t n, const u64 *alpha, const u64 *beta)
     }
 }
 
+/* proof of work, serial branch of PublicCoin::grind_proof_of_work (src/random.rs:48-51,129-132) */
+static u32 leading_zero_bits(const uint8_t d[32]) {
+    u32 z = 0;
+    for (int i = 0; i < 32; i++) {
+        if (d[i] == 0) { z += 8; continue; }
+        z += (u32)__builtin_clz((unsigned)d[i]) - 24;
+        break;
+    }
+    return z;
+}
+u64 orc_pow_grind(const uint8_t seed[32], unsigned bits) {
+    uint8_t msg[40], dig[32];
+    memcpy(msg, seed, 32);
+    for (u64 nonce = 1;; nonce++) {
+        for (int i = 0; i < 8; i++) msg[32 + i] = (uint8_t)(nonce >> (8 * (7 - i)));
+        orc_sha256(msg, 40, dig);
+        if (leading_zero_bits(dig) >= bits) return nonce;
+    }
+}
+
 /* --------------------------------------------------------- misc helpers -- */
 /* synthetic data: splitmix64, reject >= p, canonical x -> x*2^64 mod p */
 void orc_splitmix_fill(u64 *dst, size_t n, u64 seed) {

@@ -67,6 +67,8 @@ def lib():
         L.orc_divide_out_points.argtypes = [u64p, C.c_size_t, u64p, u64p, C.c_uint]
         L.orc_degree_adjust.argtypes = [u64p, C.c_size_t, u64p, u64p]
         L.orc_splitmix_fill.argtypes = [u64p, C.c_size_t, u64]
+        L.orc_pow_grind.restype = u64
+        L.orc_pow_grind.argtypes = [u8p, C.c_uint]
         L.orc_num_threads.restype = C.c_int
         L.orc_set_num_threads.argtypes = [C.c_int]
     return _lib
@@ -232,6 +234,11 @@ def degree_adjust(coeffs, alpha, beta):
     lib().orc_degree_adjust(_p(out), out.size // 3, _p(np.ascontiguousarray(alpha, dtype=np.uint64)),
                             _p(np.ascontiguousarray(beta, dtype=np.uint64)))
     return out
+
+
+def pow_grind(seed, bits):
+    a = np.frombuffer(bytes(seed), dtype=np.uint8).copy()
+    return int(lib().orc_pow_grind(_p8(a), bits))
 
 
 def num_threads():

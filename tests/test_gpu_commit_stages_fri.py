@@ -240,3 +240,10 @@ def test_config4_fri_layers_resident(ctx, orc, log_n):
         want = orc.fri_apply_drp(want, field, ln, log_ff, alpha)
         assert np.array_equal(nxt.cpu().numpy().view(np.uint64), want)
         cur = nxt
+
+
+def test_pow_grind_smallest_nonce(ctx, orc):
+    # grind_fri_commitments (src/channel.rs:76-93); brainfuck uses grinding_factor 20 (examples/brainfuck/main.rs:95)
+    for tag, bits in ((b"a", 0), (b"b", 8), (b"c", 16), (b"d", 20)):
+        seed = hashlib.sha256(tag).digest()
+        assert ctx.pow_grind(seed, bits) == orc.pow_grind(seed, bits)

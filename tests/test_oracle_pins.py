@@ -215,3 +215,15 @@ def test_deep_helpers(orc):
     base = [rng.randrange(P) for _ in range(n)]
     h = orc.from_mont(orc.horner(orc.to_mont(np.array(base, dtype=np.uint64)), 1, flat(zs[:1])))
     assert tuple(int(x) for x in h) == S.horner(base, zs[0], 1)
+
+
+def test_pow_grind_vs_hashlib(orc):
+    # PublicCoin::verify_proof_of_work (src/random.rs:129-132): leading zero bits of SHA-256(seed || nonce_be)
+    seed = hashlib.sha256(b"pow").digest()
+    for bits in (0, 1, 5, 11):
+        nonce = orc.pow_grind(seed, bits)
+        def lz(n):
+            d = hashlib.sha256(seed + n.to_bytes(8, "big")).digest()
+            return len(bin(int.from_bytes(d, "big"))) - 2 if False else 256 - int.from_bytes(d, "big").bit_length()
+        assert nonce >= 1 and lz(nonce) >= bits
+        assert all(lz(k) < bits for k in range(1, nonce))
