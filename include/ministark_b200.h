@@ -140,6 +140,14 @@ int ms_merkle_commit_rows_sha256(ms_ctx *ctx, const void *rows, unsigned row_wor
  * (deterministic, unlike the reference's rayon find_any) */
 int ms_pow_grind_sha256(ms_ctx *ctx, const uint8_t *seed, unsigned bits, uint64_t *nonce_out);
 
+/* ---- query phase: MerkleTreeImpl::prove / MatrixMerkleTree::prove_rows (src/merkle.rs:149-207,301-303) ----
+ * batched authentication paths (the reference's MerkleView) for `indices` (any order, duplicates allowed) from the
+ * resident leaf and node arrays of a committed tree.  Outputs (host): initial_leaves and sibling_leaves hold up to
+ * n_indices digests each, path_nodes up to n_indices * log2(n_leaves); counts = {initial, sibling, path} digests written */
+int ms_merkle_prove_sha256(ms_ctx *ctx, const void *leaves, const void *nodes, size_t n_leaves, const uint64_t *indices,
+                           unsigned n_indices, uint8_t *initial_leaves, uint8_t *sibling_leaves, uint8_t *path_nodes,
+                           unsigned counts[3]);
+
 /* ---- matrix plumbing ----
  * Matrix::from_arrays / from_rows (src/matrix.rs:33-64) and the composition split (src/prover.rs:113-120):
  * n rows of k elements (row-major) -> k columns of n elements */
@@ -149,6 +157,9 @@ int ms_matrix_from_rows(ms_ctx *ctx, int field, const void *rows, size_t n, unsi
  * out[q * ncols + c] = cols[c][row_ids[q]]; row_ids is a host array */
 int ms_gather_rows(ms_ctx *ctx, int field, const void *cols, size_t col_stride_elems, unsigned ncols, size_t nrows,
                    const uint64_t *row_ids, unsigned nq, void *out);
+/* query_layer (src/fri.rs:650-664): rows of a ROW-MAJOR matrix (a committed FRI layer); out[q] = rows[row_ids[q]] */
+int ms_gather_rows_rowmajor(ms_ctx *ctx, const void *rows, unsigned row_words, size_t nrows, const uint64_t *row_ids,
+                            unsigned nq, void *out);
 
 /* ---- FRI: apply_drp (src/fri.rs:526-567) evaluated per coset, bit-reversed order in and out ----
  * evals: 2^log_n elements; out: 2^(log_n-log_ff).  alpha: one element of `field`.

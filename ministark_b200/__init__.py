@@ -175,6 +175,21 @@ class Context:
         self._ck(self.lib.ms_pow_grind_sha256(self.h, sd, bits, C.byref(out)))
         return int(out.value)
 
+    def merkle_prove(self, leaves, nodes, n_leaves, indices):
+        """MerkleTreeImpl::prove (src/merkle.rs:149-207) on a resident tree.  Returns the reference's MerkleView as
+        (nodes, initial_leaves, sibling_leaves, height): three lists of 32-byte digests and log2(n_leaves)."""
+        ids = np.ascontiguousarray(indices, dtype=np.uint64)
+        height = int(n_leaves).bit_length() - 1
+        k = max(int(ids.size), 1)
+        init = np.empty((k, 32), dtype=np.uint8)
+        sib = np.empty((k, 32), dtype=np.uint8)
+        path = np.empty((k * max(height, 1), 32), dtype=np.uint8)
+        counts = (C.c_uint * 3)()
+        self._ck(self.lib.ms_merkle_prove_sha256(self.h, _ptr(leaves), _ptr(nodes), n_leaves, ids.ctypes.data, ids.size,
+                                                 init.ctypes.data, sib.ctypes.data, path.ctypes.data, counts))
+        as_list = lambda a, m: [a[i].tobytes() for i in range(m)]
+        return as_list(path, counts[2]), as_list(init, counts[0]), as_list(sib, counts[1]), height
+
     def matrix_from_rows(self, rows, cols, field, n, k, col_stride=None):
         self._ck(self.lib.ms_matrix_from_rows(self.h, field, _ptr(rows), n, k, _ptr(cols), n if col_stride is None else col_stride))
 
@@ -183,6 +198,14 @@ class Context:
         out = np.empty((ids.size, ncols * field), dtype=np.uint64)
         self._ck(self.lib.ms_gather_rows(self.h, field, _ptr(cols), nrows if col_stride is None else col_stride, ncols,
                                          nrows, ids.ctypes.data, ids.size, out.ctypes.data))
+        return out
+
+    def gather_rows_rowmajor(self, rows, row_words, nrows, row_ids):
+        """rows of a committed FRI layer (query_layer, src/fri.rs:650-664); returns (len(row_ids), row_words) words"""
+        ids = np.ascontiguousarray(row_ids, dtype=np.uint64)
+        out = np.empty((ids.size, row_words), dtype=np.uint64)
+        self._ck(self.lib.ms_gather_rows_rowmajor(self.h, _ptr(rows), row_words, nrows, ids.ctypes.data, ids.size,
+                                                  out.ctypes.data))
         return out
 
     # ---- FRI

@@ -45,8 +45,10 @@ _SIGS = {
     "ms_merkle_commit_sha256": (ci, [vp, ci, vp, sz, ui, sz, vp, vp, vp]),
     "ms_merkle_commit_rows_sha256": (ci, [vp, vp, ui, sz, vp, vp, vp]),
     "ms_pow_grind_sha256": (ci, [vp, vp, ui, C.POINTER(u64)]),
+    "ms_merkle_prove_sha256": (ci, [vp, vp, vp, sz, vp, ui, vp, vp, vp, vp]),
     "ms_matrix_from_rows": (ci, [vp, ci, vp, sz, ui, vp, sz]),
     "ms_gather_rows": (ci, [vp, ci, vp, sz, ui, sz, vp, ui, vp]),
+    "ms_gather_rows_rowmajor": (ci, [vp, vp, ui, sz, vp, ui, vp]),
     "ms_fri_fold": (ci, [vp, ci, vp, ui, ui, u64, vp, vp]),
     "ms_eval_constraints": (ci, [vp, vp, ui, vp, ui, vp, sz, ui, vp, sz, ui, ci, ui, u64, ci, ci, vp]),
     "ms_eval_constraints_ptrs": (ci, [vp, vp, ui, vp, ui, vp, vp, ui, ci, ui, u64, ci, ci, vp]),

@@ -12,6 +12,10 @@
 // one reduction, byte-swapped into the big-endian SHA message schedule and compressed.  This
 // kernel is INT32-ALU bound (about 2k instructions per 64-byte block), not HBM bound.
 #include "ctx.cuh"
+#include <algorithm>
+#include <cstring>
+#include <deque>
+#include <vector>
 
 namespace ms {
 
@@ -163,6 +167,16 @@ __global__ void __launch_bounds__(128) pow_grind_kernel(uint4 seed_lo, uint4 see
     unsigned lz = __clz(s.h[0]);
     if (s.h[0] == 0) { lz = 32 + __clz(s.h[1]); if (s.h[1] == 0) lz = 64 + __clz(s.h[2]); }
     if (lz >= bits) atomicMin(best, (unsigned long long)nonce);
+}
+
+// multiproof gather: out[q] = (sel[q] >> 63 ? nodes : leaves)[sel[q] & mask]  (32-byte digests as 2 x uint4)
+__global__ void gather_digests_kernel(const uint4 *__restrict__ leaves, const uint4 *__restrict__ nodes, const u64 *__restrict__ sel,
+                                      unsigned count, uint4 *__restrict__ out) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * count) return;
+    const u64 s = sel[t >> 1];
+    const uint4 *src = (s >> 63) ? nodes : leaves;
+    out[t] = src[2 * (s & ~(1ull << 63)) + (t & 1)];
 }
 
 static int upload_row_pad_schedule(ms_ctx *c, unsigned row_words);
@@ -380,6 +394,76 @@ int ms_pow_grind_sha256(ms_ctx *c, const uint8_t *seed, unsigned bits, uint64_t 
         }
         if (base > (~0ull) - 2 * batch) return fail(c, MS_ERR_INVALID, "nonce not found");   // .expect("nonce not found")
     }
+}
+
+// MerkleTreeImpl::prove (src/merkle.rs:149-207): batched authentication paths for a set of leaves, read from the
+// RESIDENT leaf and node arrays — only the <= n_indices * (height + 1) digests of the proof cross PCIe.
+// The index walk (two queues, siblings merged when both are in the set) runs on the host; one gather kernel
+// fetches every digest the walk names.
+int ms_merkle_prove_sha256(ms_ctx *c, const void *leaves, const void *nodes, size_t n_leaves, const uint64_t *indices,
+                           unsigned n_indices, uint8_t *initial_leaves, uint8_t *sibling_leaves, uint8_t *path_nodes,
+                           unsigned counts[3]) {
+    if (!c || !leaves || !nodes || !indices || !initial_leaves || !sibling_leaves || !path_nodes || !counts) return MS_ERR_INVALID;
+    if (n_leaves < 2 || (n_leaves & (n_leaves - 1))) return fail(c, MS_ERR_INVALID, "ms_merkle_prove: leaf count must be a power of two >= 2");
+    cudaSetDevice(c->device);
+    std::vector<u64> idx(indices, indices + n_indices);
+    for (u64 i : idx)
+        if (i >= n_leaves) return fail(c, MS_ERR_INVALID, "leaf index `%llu` cannot exceed the number of leaves (`%llu`)",
+                                       (unsigned long long)i, (unsigned long long)n_leaves);
+    std::sort(idx.begin(), idx.end());
+    idx.erase(std::unique(idx.begin(), idx.end()), idx.end());
+    const u64 NODE = 1ull << 63;
+    std::vector<u64> init, sib, path;
+    std::deque<u64> node_q;
+    for (size_t k = 0; k < idx.size(); k++) {
+        const u64 i = idx[k];
+        init.push_back(i);
+        node_q.push_back((n_leaves + i) >> 1);
+        if (k + 1 < idx.size() && (i ^ 1) == idx[k + 1]) {
+            init.push_back(idx[++k]);
+            continue;
+        }
+        sib.push_back(i ^ 1);
+    }
+    while (!node_q.empty()) {
+        const u64 i = node_q.front();
+        node_q.pop_front();
+        if (i > 2) node_q.push_back(i >> 1);
+        if (!node_q.empty() && (i ^ 1) == node_q.front()) {
+            node_q.pop_front();
+            continue;
+        }
+        path.push_back((i ^ 1) | NODE);      // (n_leaves == 2 names nodes[0], the unused default digest, as the reference does)
+    }
+    counts[0] = (unsigned)init.size();
+    counts[1] = (unsigned)sib.size();
+    counts[2] = (unsigned)path.size();
+    std::vector<u64> sel(init);
+    sel.insert(sel.end(), sib.begin(), sib.end());
+    sel.insert(sel.end(), path.begin(), path.end());
+    const unsigned total = (unsigned)sel.size();
+    if (!total) return MS_OK;
+    Staged lv(c, leaves, n_leaves * 32, true, false);
+    if (lv.rc) return lv.rc;
+    Staged nd(c, nodes, n_leaves * 32, true, false);
+    if (nd.rc) return nd.rc;
+    void *dsel, *dout;
+    int rc;
+    if ((rc = scratch_get(c, 2, (size_t)total * 8, &dsel))) return rc;
+    if ((rc = scratch_get(c, 3, (size_t)total * 32, &dout))) return rc;
+    MS_CUDA(c, cudaMemcpyAsync(dsel, sel.data(), (size_t)total * 8, cudaMemcpyHostToDevice, c->stream));
+    gather_digests_kernel<<<(2 * total + 127) / 128, 128, 0, c->stream>>>(lv.as<uint4>(), nd.as<uint4>(), (const u64 *)dsel, total,
+                                                                           (uint4 *)dout);
+    c->launches++;
+    MS_CHECK_LAUNCH(c);
+    std::vector<uint8_t> host((size_t)total * 32);
+    MS_CUDA(c, cudaMemcpyAsync(host.data(), dout, host.size(), cudaMemcpyDeviceToHost, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    memcpy(initial_leaves, host.data(), init.size() * 32);
+    memcpy(sibling_leaves, host.data() + init.size() * 32, sib.size() * 32);
+    memcpy(path_nodes, host.data() + (init.size() + sib.size()) * 32, path.size() * 32);
+    if ((rc = lv.finish())) return rc;
+    return nd.finish();
 }
 
 }  // extern "C"

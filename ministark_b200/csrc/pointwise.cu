@@ -9,6 +9,7 @@
 // one AddAssign dispatch per column.
 // These are streaming kernels (HBM bound): one element per thread, grid sized to cover n.
 #include "ctx.cuh"
+#include <vector>
 
 namespace ms {
 
@@ -273,6 +274,35 @@ int ms_gather_rows(ms_ctx *c, int field, const void *cols, size_t col_stride_ele
     const unsigned total = nq * ncols;
     gather_rows_kernel<<<(total + 127) / 128, 128, 0, c->stream>>>(in.as<u64>(), col_stride_elems * field, ncols, (unsigned)field,
                                                                     (const u64 *)ids, nq, o.as<u64>());
+    c->launches++;
+    MS_CHECK_LAUNCH(c);
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if ((rc = in.finish())) return rc;
+    return o.finish();
+}
+
+// query_layer (src/fri.rs:650-664): rows of a committed FRI layer, which is kept ROW-MAJOR (row k = the ff consecutive
+// evaluations of coset k, as ms_merkle_commit_rows_sha256 hashed them).  out[q] = rows[row_ids[q]] (row_words words each).
+int ms_gather_rows_rowmajor(ms_ctx *c, const void *rows, unsigned row_words, size_t nrows, const uint64_t *row_ids, unsigned nq,
+                            void *out) {
+    if (!c || !rows || !row_ids || !out) return MS_ERR_INVALID;
+    if (row_words == 0 || nq == 0) return MS_OK;
+    std::vector<u64> first(nq);
+    for (unsigned q = 0; q < nq; q++) {
+        if (row_ids[q] >= nrows) return fail(c, MS_ERR_INVALID, "ms_gather_rows_rowmajor: row %llu out of range", (unsigned long long)row_ids[q]);
+        first[q] = row_ids[q] * row_words;
+    }
+    Staged in(c, rows, nrows * row_words * 8, true, false);
+    if (in.rc) return in.rc;
+    Staged o(c, out, (size_t)nq * row_words * 8, false, true);
+    if (o.rc) return o.rc;
+    void *ids;
+    int rc = scratch_get(c, 3, (size_t)nq * 8, &ids);
+    if (rc) return rc;
+    MS_CUDA(c, cudaMemcpyAsync(ids, first.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, c->stream));
+    // word (q, w) = rows[first[q] + w]: the column-major gather with one-word "columns" of stride 1
+    const unsigned total = nq * row_words;
+    gather_rows_kernel<<<(total + 127) / 128, 128, 0, c->stream>>>(in.as<u64>(), 1, row_words, 1u, (const u64 *)ids, nq, o.as<u64>());
     c->launches++;
     MS_CHECK_LAUNCH(c);
     MS_CUDA(c, cudaStreamSynchronize(c->stream));

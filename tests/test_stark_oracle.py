@@ -1,0 +1,133 @@
+"""CPU-only: the restated protocol layer (oracle/stark_oracle.py) is self-consistent — the reference-formulation CPU
+prover's bytes are accepted by the restated `default_verify`, any tampering is rejected — and the product's host-side
+Fiat–Shamir code (ministark_b200/channel.py, air.py) agrees with the oracle's independent implementation.
+Mirrors the reference's own end-to-end check (examples/fib/main.rs:227-243: prove, then verify) and
+src/merkle.rs:528-581 (prove/verify round trips)."""
+import hashlib
+import random
+
+import numpy as np
+import pytest
+
+from ministark_b200 import channel as CH
+from ministark_b200.air import Air, ProofOptions, blowup_factor, degree
+from ministark_b200 import expr as E
+from ministark_b200.examples import fib, perm
+from oracle import stark_oracle as SO
+
+
+def air_factory(stark):
+    return lambda n, o: Air(stark.AirConfig, n, stark.get_public_inputs(), ProofOptions(*o))
+
+
+@pytest.mark.parametrize("log_rows,opts", [(7, (32, 4, 8, 8, 64)), (9, (20, 8, 5, 4, 16)), (6, (10, 2, 0, 2, 8)), (8, (16, 16, 3, 16, 4))])
+def test_fib_cpu_prove_verify(orc, log_rows, opts):
+    trace, last = fib.gen_trace(8 << log_rows)
+    claim = fib.FibClaim(last)
+    proof = SO.cpu_prove(claim, opts, trace.base_columns(), air_factory(claim))
+    art = SO.verify(claim, proof, 10, air_factory(claim))
+    assert len(art["query_positions"]) <= opts[0] and art["query_positions"] == sorted(set(art["query_positions"]))
+    # a wrong public input fails at the OOD consistency check (verifier.rs:84-86)
+    bad = fib.FibClaim((last + 1) % fib.P)
+    with pytest.raises(SO.VerificationError, match="out-of-domain"):
+        SO.verify(bad, proof, 10, air_factory(bad))
+    # insufficient security is refused up front (verifier.rs:34-36)
+    with pytest.raises(SO.VerificationError, match="security"):
+        SO.verify(claim, proof, 129, air_factory(claim))
+    # every single-bit corruption of the proof is rejected (sampled)
+    rng = random.Random(log_rows)
+    for _ in range(40):
+        b = bytearray(proof)
+        i = rng.randrange(5, len(b))
+        b[i] ^= 1 << rng.randrange(8)
+        with pytest.raises((SO.VerificationError, ValueError)):
+            SO.verify(claim, bytes(b), 10, air_factory(claim))
+
+
+def test_fib_trace_satisfies_recurrence():
+    trace, last = fib.gen_trace(1 << 12)
+    cols = [[int(w) * pow(2**64, -1, fib.P) % fib.P for w in c] for c in trace.base_columns()]
+    flat = [cols[k][r] for r in range(len(cols[0])) for k in range(8)]
+    assert flat[0] == 1 and flat[1] == 2 and flat[-1] == last
+    assert all(flat[k] == flat[k - 2] * flat[k - 1] % fib.P for k in range(2, len(flat)))
+
+
+def test_invalid_trace_is_rejected_by_the_verifier(orc):
+    # the prover never checks the AIR (src/debug.rs is debug-only) and every polynomial it commits to is low degree by
+    # construction, so a bad trace still yields a proof — which the verifier's OOD consistency check refuses
+    trace, last = fib.gen_trace(8 << 6)
+    cols = trace.base_columns().copy()
+    cols[3, 17] ^= np.uint64(1)
+    claim = fib.FibClaim(last)
+    proof = SO.cpu_prove(claim, (10, 4, 0, 8, 4), cols, air_factory(claim))
+    with pytest.raises(SO.VerificationError, match="out-of-domain"):
+        SO.verify(claim, proof, 10, air_factory(claim))
+
+
+@pytest.mark.parametrize("log_n,opts", [(6, (12, 8, 4, 4, 8)), (8, (20, 16, 6, 16, 4))])
+def test_perm_fq3_cpu_prove_verify(orc, log_n, opts):
+    claim = perm.PermClaim()
+    tr = perm.gen_trace(1 << log_n)
+    air = air_factory(claim)(1 << log_n, opts)
+    assert air.ce_blowup_factor == 4 and air.num_challenges() == 1
+    proof = SO.cpu_prove(claim, opts, tr.base_columns(), air_factory(claim), ext_builder=tr.build_extension_columns)
+    SO.verify(claim, proof, 10, air_factory(claim))
+    rng = random.Random(log_n)
+    for _ in range(25):
+        b = bytearray(proof)
+        b[rng.randrange(5, len(b))] ^= 1 << rng.randrange(8)
+        with pytest.raises((SO.VerificationError, ValueError)):
+            SO.verify(claim, bytes(b), 10, air_factory(claim))
+
+
+def test_degree_rules_match_the_reference_examples():
+    # examples/fib: every constraint and the composition have blowup 1 (SURVEY.md §8d config 3 note)
+    n = 1 << 10
+    cs = fib.FibAirConfig.constraints(n)
+    assert [blowup_factor(c, n) for c in cs] == [1] * 17
+    assert degree(cs[0], n - 1) == (n - 1, 1) and degree(cs[9], n - 1) == (2 * (n - 1) + 1, n)
+    air = Air(fib.FibAirConfig, n, 0, fib.OPTIONS)
+    assert air.ce_blowup_factor == 1 and air.num_composition_constraint_coeffs() == 34
+    assert air.trace_arguments() == [(c, o) for c in range(8) for o in (0, 1)]
+    # tests/constraint.rs:199-217: x*(x-1) has degree 2(n-1)
+    c = E.Trace(0, 0) * (E.Trace(0, 0) - E.Constant(1))
+    assert degree(c, n - 1) == (2 * (n - 1), 0)
+
+
+def test_public_coin_two_implementations_agree():
+    seed = hashlib.sha256(b"coin").digest()
+    for ext in (False, True):
+        a, b = CH.PublicCoin(seed, ext=ext), SO.Coin(seed, 3 if ext else 1)
+        for step in range(40):
+            va, vb = a.draw(), b.draw()
+            assert SO.q(va) == vb
+            if step % 7 == 3:
+                d = hashlib.sha256(bytes([step])).digest()
+                a.reseed_with_digest(d); b.reseed_digest(d)
+            if step % 11 == 5:
+                a.reseed_with_field_elements([va, va]); b.reseed_elements([vb, vb])
+            if step % 13 == 6:
+                a.reseed_with_int(step * 1234567); b.reseed_int(step * 1234567)
+        assert a.draw_queries(32, 1 << 23) == b.draw_queries(32, 1 << 23)
+        assert a.draw_queries(5, 96) == b.draw_queries(5, 96)          # non power of two range: zone rejection path
+        for nonce in range(1, 200):
+            assert a.verify_proof_of_work(4, nonce) == b.check_pow(4, nonce)
+    # byte order of the coin: bytes are popped from the end of SHA-256(seed || counter_be), assembled big-endian
+    c = CH.PublicCoin(seed)
+    d = hashlib.sha256(seed + (1).to_bytes(8, "big")).digest()
+    assert c.next_u64() == int.from_bytes(d[::-1][:8], "big")
+
+
+def test_merkle_view_roundtrip_like_reference(orc):
+    # src/merkle.rs:528-581: prove then verify, single leaf / all leaves / large tree
+    rng = np.random.default_rng(3)
+    for n, ids in ((8, [3]), (4, [0, 1, 2, 3]), (1 << 10, [378]), (64, [5, 4, 63, 17, 16, 5]), (2, [1])):
+        leaves = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        nodes = orc.merkle_nodes(leaves)
+        view = SO._merkle_prove(leaves, nodes, ids)
+        SO.merkle_verify(nodes[1].tobytes(), view, ids)
+        if n > 2:
+            key = "nodes" if view["nodes"] else "initial_leaves"     # all leaves opened: there are no path nodes
+            view[key][0] = bytes(32)
+            with pytest.raises(SO.VerificationError):
+                SO.merkle_verify(nodes[1].tobytes(), view, ids)
