@@ -159,6 +159,19 @@ def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, lo
     order, seen = [], set()
 
     def visit(e):                      # iterative post-order (DAGs can be deep)
+        # Sethi-Ullman flavoured order: the operand with the larger subtree is evaluated first, so a long
+        # left-deep sum of constraint terms keeps one accumulator live instead of every term
+        size, st = {}, [(e, False)]
+        while st:
+            node, done = st.pop()
+            if done:
+                size[id(node)] = 1 + sum(size[id(a)] for a in node.args if isinstance(a, Expr))
+                continue
+            if id(node) in size:
+                continue
+            size[id(node)] = 0
+            st.append((node, True))
+            st.extend((a, False) for a in node.args if isinstance(a, Expr) and id(a) not in size)
         stack = [(e, False)]
         while stack:
             node, done = stack.pop()
@@ -169,9 +182,10 @@ def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, lo
                 continue
             seen.add(id(node))
             stack.append((node, True))
-            for a in node.args:
-                if isinstance(a, Expr) and id(a) not in seen:
-                    stack.append((a, False))
+            kids = [a for a in node.args if isinstance(a, Expr) and id(a) not in seen]
+            kids.sort(key=lambda a: size[id(a)])          # popped last-in first-out: largest subtree first
+            for a in kids:
+                stack.append((a, False))
 
     # a / b  ->  a * inv(b) with inv(b) hash-consed, so a denominator shared by many constraints
     # (the zerofier X^n - 1) is inverted once per point instead of once per Div node
@@ -247,47 +261,64 @@ def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, lo
         return const_idx[v]
 
     code, reg_of, free, nregs = [], {}, [], 0
+    # Leaves (x, trace loads, constants) are rematerialisable: when the register file is full the least recently used
+    # one is dropped and simply loaded again at its next use (large AIRs such as examples/brainfuck touch ~50 distinct
+    # trace cells from dozens of constraints).  Interior temporaries are never evicted.
+    leaf_regs, pinned, touch = {}, set(), {}
+
+    def is_leaf(x):
+        return id(x) in cval or x.kind in ("x", "trace")
 
     def alloc():
         nonlocal nregs
         if free:
             return free.pop()
-        nregs += 1
-        if nregs > MAX_REGS:
+        if nregs < MAX_REGS:
+            nregs += 1
+            return nregs - 1
+        victims = [k for k in leaf_regs if k not in pinned]
+        if not victims:
             raise ValueError(f"expression needs more than {MAX_REGS} live temporaries")
-        return nregs - 1
+        k = min(victims, key=lambda v: touch.get(v, -1))
+        del leaf_regs[k]
+        return reg_of.pop(k)
+
+    def emit_leaf(x):
+        r = alloc()
+        if id(x) in cval:
+            code.append([OP_CONST | (typ[id(x)] << 8), r, const_slot(cval[id(x)]), 0])
+        elif x.kind == "x":
+            code.append([OP_X, r, 0, 0])
+        else:
+            col, off = x.args
+            shift = lde_step * off
+            if log_ce is not None:
+                shift %= (1 << log_ce)
+            code.append([OP_TRACE | (int(col >= num_base_cols) << 8), r, col, shift & 0xFFFFFFFF])
+        reg_of[id(x)] = r
+        leaf_regs[id(x)] = x
+        return r
 
     def operand(x):
-        """register holding node x (materialising folded constants on demand)"""
-        if id(x) in reg_of:
-            return reg_of[id(x)]
-        r = alloc()
-        code.append([OP_CONST | (typ[id(x)] << 8), r, const_slot(cval[id(x)]), 0])
-        reg_of[id(x)] = r
+        """register holding node x (materialising constants and evicted leaves on demand); pins it for this instruction"""
+        r = reg_of[id(x)] if id(x) in reg_of else emit_leaf(x)
+        pinned.add(id(x))
+        touch[id(x)] = len(code)
         return r
 
     def release(x, idx):
         if last_use.get(id(x)) == idx and id(x) in reg_of:
             free.append(reg_of.pop(id(x)))
+            leaf_regs.pop(id(x), None)
 
     for idx, nd in enumerate(live_nodes):
         k, a = nd.kind, nd.args
-        t = typ[id(nd)]
-        if id(nd) in cval:            # the root itself is a constant
-            operand(nd)
-            continue
-        if k == "x":
-            r = alloc()
-            code.append([OP_X, r, 0, 0])
-        elif k == "trace":
-            col, off = a
-            is_q = col >= num_base_cols
-            shift = (lde_step * off)
-            if log_ce is not None:
-                shift %= (1 << log_ce)
-            r = alloc()
-            code.append([OP_TRACE | (int(is_q) << 8), r, col, shift & 0xFFFFFFFF])
-        elif k == "neg":
+        pinned.clear()
+        if is_leaf(nd):
+            if nd is expr:            # the root itself is a leaf / constant
+                operand(nd)
+            continue                  # loaded lazily at first use
+        if k == "neg":
             ra = operand(a[0])
             release(a[0], idx)
             r = alloc()

@@ -102,3 +102,18 @@ def test_gather_rows_rowmajor():
     assert np.array_equal(ctx.gather_rows_rowmajor(rows, 24, 4096, ids), rows[ids])
     with pytest.raises(ms.MsError):
         ctx.gather_rows_rowmajor(rows, 24, 4096, [4096])
+
+
+def test_brainfuck_hello_world_proof_bytes_match_cpu_prover(prover, orc):
+    """BASELINE config 2: brainfuck hello_world.bf, full prove -> verify, proof bytes identical to the CPU path"""
+    from oracle import stark_oracle as SO
+    from ministark_b200.examples import brainfuck as bf
+    trace, out = bf.simulate(bf.HELLO_WORLD)
+    claim = bf.BrainfuckClaim(bf.HELLO_WORLD, b"", out)
+    mk = lambda n, o: Air(claim.AirConfig, n, claim, ProofOptions(*o))
+    proof = prover.prove(claim, bf.OPTIONS, trace)
+    got = proof.to_bytes()
+    want = SO.cpu_prove(claim, (19, 16, 20, 16, 16), trace.base_columns(), mk, ext_builder=trace.build_extension_columns)
+    assert got == want
+    SO.verify(claim, got, bf.SECURITY_LEVEL, mk)
+    assert proof.pow_nonce > 0 and len(proof.fri_proof.layers) == 2

@@ -131,3 +131,39 @@ def test_merkle_view_roundtrip_like_reference(orc):
             view[key][0] = bytes(32)
             with pytest.raises(SO.VerificationError):
                 SO.merkle_verify(nodes[1].tobytes(), view, ids)
+
+
+def test_brainfuck_hello_world_cpu_prove_verify(orc):
+    """BASELINE config 2: examples/brainfuck hello_world.bf with the reference's ProofOptions(19, 16, 20, 16, 16).
+    SURVEY.md §8d: 108 program words, n = 2048, 17 Fp + 9 Fq3 columns, ce_blowup 16."""
+    from ministark_b200.examples import brainfuck as bf
+    trace, out = bf.simulate(bf.HELLO_WORLD)
+    assert out == b"Hello World" and len(trace) == 2048 and len(bf.compile_program(bf.HELLO_WORLD)) == 108
+    assert trace.base_columns().shape == (17, 2048)
+    claim = bf.BrainfuckClaim(bf.HELLO_WORLD, b"", out)
+    mk = lambda n, o: Air(claim.AirConfig, n, claim, ProofOptions(*o))
+    air = mk(2048, (19, 16, 20, 16, 16))
+    assert air.ce_blowup_factor == 16 and air.num_challenges() == 11 and len(air.constraints) == 48
+    proof = SO.cpu_prove(claim, (19, 16, 20, 16, 16), trace.base_columns(), mk, ext_builder=trace.build_extension_columns)
+    SO.verify(claim, proof, bf.SECURITY_LEVEL, mk)
+    pr = SO.parse_proof(proof, 3)
+    assert len(pr["fri_layers"]) == 2 and len(pr["remainder"]) == 8            # 32768 -> 2048 -> 128 evals -> 8 coefficients
+    bad = bf.BrainfuckClaim(bf.HELLO_WORLD, b"", b"Hello World?")
+    with pytest.raises(SO.VerificationError):
+        SO.verify(bad, proof, bf.SECURITY_LEVEL, lambda n, o: Air(bad.AirConfig, n, bad, ProofOptions(*o)))
+
+
+def test_brainfuck_vm_with_input():
+    from ministark_b200.examples import brainfuck as bf
+    trace, out = bf.simulate(",>,<.>.", b"hi")           # echo two bytes
+    assert out == b"hi"
+    rows = trace.rows
+    assert sum(1 for r in rows if r[bf.CURR_INSTR] == bf.READ) == 2
+    assert [r[bf.IN_VALUE] for r in rows[:3]] == [ord("h"), ord("i"), 0]
+    # ChaCha (test_rng restatement): the quarter-round core reproduces the RFC 7539 section 2.3.2 block (20 rounds)
+    key = [int.from_bytes(bytes(range(4 * i, 4 * i + 4)), "little") for i in range(8)]
+    st = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574] + key + [1, 0x09000000, 0x4A000000, 0]
+    w = bf._chacha_core(st, 20)
+    assert w[:4] == [0xE4E7F110, 0x15593BD1, 0x1FDD0F50, 0xC47120A3] and w[15] == 0x4E3C50A2
+    a, b = bf.test_rng_fq3(2)
+    assert a != b and all(0 <= c < bf.P for c in a + b)
