@@ -46,7 +46,40 @@ __constant__ u32 c_KW_pad64[64];
 // same for the padding block that follows a leaf row whose length is a multiple of 64 bytes (set per launch)
 __constant__ u32 c_KW_padrow[64];
 
-struct Sha {
+// Pipe balancing: SHF/LOP3/IADD3 all issue on the 64-lane ALU pipe while the FMA pipe idles.  fma_add() forces
+// an addition onto the FMA pipe as IMAD (x * c_one + y); c_one lives in constant memory so ptxas cannot fold it
+// back into an IADD3.  V is a bit mask: 1 message-schedule adds, 2 the t1 chain, 4 t2 / e / a, 8 K+W, 16 sigma shifts.
+__constant__ u32 c_one = 1;
+template <int ON>
+__device__ __forceinline__ u32 fma_add(u32 a, u32 b) {
+    if constexpr (ON) {
+        u32 d;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(c_one), "r"(b));
+        return d;
+    } else {
+        return a + b;
+    }
+}
+
+// logical right shift on the FMA pipe: x >> r = mulhi(x, 2^(32-r)), the multiplier read from constant memory
+__constant__ u32 c_pow2[33] = {0, 1u << 31, 1u << 30, 1u << 29, 1u << 28, 1u << 27, 1u << 26, 1u << 25, 1u << 24, 1u << 23, 1u << 22,
+                               1u << 21, 1u << 20, 1u << 19, 1u << 18, 1u << 17, 1u << 16, 1u << 15, 1u << 14, 1u << 13, 1u << 12,
+                               1u << 11, 1u << 10, 1u << 9, 1u << 8, 1u << 7, 1u << 6, 1u << 5, 1u << 4, 1u << 3, 1u << 2, 1u << 1, 1};
+template <int ON, int R>
+__device__ __forceinline__ u32 shr_fma(u32 x) {
+    if constexpr (ON) {
+        u32 d;
+        asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(x), "r"(c_pow2[R]));
+        return d;
+    } else {
+        return x >> R;
+    }
+}
+template <int V> __device__ __forceinline__ u32 small_sigma0_v(u32 w) { return rotr(w, 7) ^ rotr(w, 18) ^ shr_fma<((V & 16) != 0), 3>(w); }
+template <int V> __device__ __forceinline__ u32 small_sigma1_v(u32 w) { return rotr(w, 17) ^ rotr(w, 19) ^ shr_fma<((V & 16) != 0), 10>(w); }
+
+template <int V>
+struct ShaT {
     u32 h[8];
     __device__ __forceinline__ void init() {
         h[0] = 0x6a09e667; h[1] = 0xbb67ae85; h[2] = 0x3c6ef372; h[3] = 0xa54ff53a;
@@ -58,12 +91,13 @@ struct Sha {
 #pragma unroll
         for (int i = 0; i < 64; i++) {
             if (i >= 16)
-                w[i & 15] = w[i & 15] + small_sigma0(w[(i + 1) & 15]) + w[(i + 9) & 15] + small_sigma1(w[(i + 14) & 15]);
+                w[i & 15] = fma_add<((V & 1) != 0)>(fma_add<((V & 1) != 0)>(w[i & 15], small_sigma0_v<V>(w[(i + 1) & 15])),
+                                              fma_add<((V & 1) != 0)>(w[(i + 9) & 15], small_sigma1_v<V>(w[(i + 14) & 15])));
             u32 ch = (e & f) ^ (~e & g);
-            u32 t1 = hh + big_sigma1(e) + ch + c_K[i] + w[i & 15];
+            u32 t1 = fma_add<((V & 2) != 0)>(fma_add<((V & 2) != 0)>(hh, big_sigma1(e)), fma_add<((V & 2) != 0)>(ch, fma_add<((V & 8) != 0)>(w[i & 15], c_K[i])));
             u32 mj = (a & b) ^ (a & c) ^ (b & c);
-            u32 t2 = big_sigma0(a) + mj;
-            hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+            u32 t2 = fma_add<((V & 4) != 0)>(big_sigma0(a), mj);
+            hh = g; g = f; f = e; e = fma_add<((V & 4) != 0)>(d, t1); d = c; c = b; b = a; a = fma_add<((V & 4) != 0)>(t1, t2);
         }
         h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
     }
@@ -74,10 +108,10 @@ struct Sha {
 #pragma unroll
         for (int i = 0; i < 64; i++) {
             u32 ch = (e & f) ^ (~e & g);
-            u32 t1 = hh + big_sigma1(e) + ch + kw[i];
+            u32 t1 = fma_add<((V & 2) != 0)>(fma_add<((V & 2) != 0)>(hh, big_sigma1(e)), fma_add<((V & 8) != 0)>(ch, kw[i]));
             u32 mj = (a & b) ^ (a & c) ^ (b & c);
-            u32 t2 = big_sigma0(a) + mj;
-            hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+            u32 t2 = fma_add<((V & 4) != 0)>(big_sigma0(a), mj);
+            hh = g; g = f; f = e; e = fma_add<((V & 4) != 0)>(d, t1); d = c; c = b; b = a; a = fma_add<((V & 4) != 0)>(t1, t2);
         }
         h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
     }
@@ -90,14 +124,17 @@ struct Sha {
     }
 };
 
+using Sha = ShaT<0>;
+
 // words_per_row = ncols * lanes 64-bit words; word t of row i lives at
 // cols[(t / lanes) * col_stride_words + i * lanes + t % lanes].
+template <int V>
 __global__ void __launch_bounds__(128) hash_rows_kernel(const u64 *__restrict__ cols, size_t col_stride_words,
                                                          unsigned lanes, unsigned words_per_row, size_t nrows,
                                                          u32 *__restrict__ digests, int const_pad) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= nrows) return;
-    Sha s;
+    ShaT<V> s;
     s.init();
     const unsigned msg_words32 = words_per_row * 2;
     const unsigned total32 = ((msg_words32 + 1 + 2 + 15) / 16) * 16;  // 0x80 marker + 64-bit length
@@ -131,11 +168,12 @@ __global__ void __launch_bounds__(128) hash_rows_kernel(const u64 *__restrict__ 
 }
 
 // dst[k] = SHA-256(src[2k] || src[2k+1]) for k in [0, count): one Merkle level.
+template <int V>
 __global__ void __launch_bounds__(128) merkle_level_kernel(const u32 *__restrict__ src, u32 *__restrict__ dst,
                                                             size_t count) {
     const size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (k >= count) return;
-    Sha s;
+    ShaT<V> s;
     s.init();
     u32 w[16];
     const uint4 *p = reinterpret_cast<const uint4 *>(src + k * 16);
@@ -179,14 +217,29 @@ __global__ void gather_digests_kernel(const uint4 *__restrict__ leaves, const ui
     out[t] = src[2 * (s & ~(1ull << 63)) + (t & 1)];
 }
 
+// MS_SHA_FMA_ADDS=0 keeps every addition on the ALU pipe (the compiler's choice); the default mask 7 moves the
+// schedule and round-function additions to the FMA pipe.  Measured on a B200, commit of 2^26 x 32 Fp rows:
+// mask 0: 32.3 ms, 1: 31.9, 3: 29.9, 7: 28.9, 15 (K+W too): 31.1, 23 (sigma shifts as IMAD.HI): 29.1.
+static int sha_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MS_SHA_FMA_ADDS");
+        v = (e && atoi(e) == 0) ? 0 : 7;
+    }
+    return v;
+}
+#define MS_SHA_DISPATCH(KERNEL, GRID, ...)                                        \
+    if (sha_variant() == 0) KERNEL<0><<<GRID, 128, 0, c->stream>>>(__VA_ARGS__);   \
+    else KERNEL<7><<<GRID, 128, 0, c->stream>>>(__VA_ARGS__);
+
 static int upload_row_pad_schedule(ms_ctx *c, unsigned row_words);
 static int hash_rows_dev(ms_ctx *c, int field, const u64 *cols, size_t col_stride_elems, unsigned ncols, size_t nrows,
                          u32 *digests) {
     if (nrows == 0) return MS_OK;
     const unsigned threads = 128;
     const int const_pad = upload_row_pad_schedule(c, ncols * field);
-    hash_rows_kernel<<<(unsigned)((nrows + threads - 1) / threads), threads, 0, c->stream>>>(
-        cols, col_stride_elems * field, (unsigned)field, ncols * field, nrows, digests, const_pad);
+    MS_SHA_DISPATCH(hash_rows_kernel, (unsigned)((nrows + threads - 1) / threads), cols, col_stride_elems * field, (unsigned)field,
+                    ncols * field, nrows, digests, const_pad);
     c->launches++;
     MS_CHECK_LAUNCH(c);
     return MS_OK;
@@ -252,14 +305,12 @@ static int merkle_nodes_dev(ms_ctx *c, const u32 *leaves, size_t n, u32 *nodes) 
     MS_CUDA(c, cudaMemsetAsync(nodes, 0, 32, c->stream));
     const unsigned threads = 128;
     // leaf pairs -> nodes[n/2 .. n)
-    merkle_level_kernel<<<(unsigned)((n / 2 + threads - 1) / threads), threads, 0, c->stream>>>(leaves, nodes + (n / 2) * 8,
-                                                                                                n / 2);
+    MS_SHA_DISPATCH(merkle_level_kernel, (unsigned)((n / 2 + threads - 1) / threads), leaves, nodes + (n / 2) * 8, n / 2);
     c->launches++;
     MS_CHECK_LAUNCH(c);
     for (size_t size = n / 4; size >= 1; size >>= 1) {
         // nodes[size .. 2 size) from nodes[2 size .. 4 size)
-        merkle_level_kernel<<<(unsigned)((size + threads - 1) / threads), threads, 0, c->stream>>>(
-            nodes + 2 * size * 8, nodes + size * 8, size);
+        MS_SHA_DISPATCH(merkle_level_kernel, (unsigned)((size + threads - 1) / threads), nodes + 2 * size * 8, nodes + size * 8, size);
         c->launches++;
         MS_CHECK_LAUNCH(c);
     }
@@ -353,8 +404,8 @@ int ms_merkle_commit_rows_sha256(ms_ctx *c, const void *rows, unsigned row_words
     // one "column" whose element is the whole row: word t of row i at base + i*row_words + t
     const unsigned threads = 128;
     const int const_pad = upload_row_pad_schedule(c, row_words);
-    hash_rows_kernel<<<(unsigned)((nrows + threads - 1) / threads), threads, 0, c->stream>>>(in.as<u64>(), 0, row_words, row_words,
-                                                                                              nrows, (u32 *)lv, const_pad);
+    MS_SHA_DISPATCH(hash_rows_kernel, (unsigned)((nrows + threads - 1) / threads), in.as<u64>(), (size_t)0, row_words, row_words, nrows,
+                    (u32 *)lv, const_pad);
     c->launches++;
     MS_CHECK_LAUNCH(c);
     if ((rc = merkle_nodes_dev(c, (const u32 *)lv, nrows, (u32 *)nd))) return rc;
