@@ -161,6 +161,14 @@ int ms_gather_rows(ms_ctx *ctx, int field, const void *cols, size_t col_stride_e
 int ms_gather_rows_rowmajor(ms_ctx *ctx, const void *rows, unsigned row_words, size_t nrows, const uint64_t *row_ids,
                             unsigned nq, void *out);
 
+/* ---- trace generation: running products / running evaluations as a parallel scan ----
+ * the sequential column builders of examples/brainfuck/trace.rs:108-279 and examples/fib/main.rs:175-222:
+ *     x_0 = init,  x_(i+1) = x_i * a_i + b_i,      out[i] = x_i (inclusive == 0) or x_(i+1) (inclusive != 0)
+ * field: type of x / out / init (MS_FIELD_FP or MS_FIELD_FQ3).  a: n elements of a_field (Fp or `field`), or NULL for
+ * the constant multiplier a_const (one element of `field`).  b: n elements of b_field, or NULL for 0. */
+int ms_scan_affine(ms_ctx *ctx, int field, const void *a, int a_field, const uint64_t *a_const, const void *b, int b_field,
+                   size_t n, const uint64_t *init, int inclusive, void *out);
+
 /* ---- FRI: apply_drp (src/fri.rs:526-567) evaluated per coset, bit-reversed order in and out ----
  * evals: 2^log_n elements; out: 2^(log_n-log_ff).  alpha: one element of `field`.
  * Equals bit_reverse ∘ NTT ∘ fold ∘ (·ff) ∘ iNTT ∘ bit_reverse of the reference, in one pass. */

@@ -208,6 +208,14 @@ class Context:
                                                   out.ctypes.data))
         return out
 
+    def scan_affine(self, out, field, n, init, a=None, a_field=FP, a_const=None, b=None, b_field=FP, inclusive=False):
+        """x_0 = init, x_(i+1) = x_i * a_i + b_i; out[i] = x_i (or x_(i+1) if inclusive) — running products and
+        running evaluations of trace columns as one parallel scan (examples/brainfuck/trace.rs:108-279)."""
+        w = lambda v: None if v is None else np.ascontiguousarray(v, dtype=np.uint64)
+        ini, ac = w(init), w(a_const)
+        self._ck(self.lib.ms_scan_affine(self.h, field, _ptr(a), a_field, None if ac is None else ac.ctypes.data,
+                                         _ptr(b), b_field, n, ini.ctypes.data, int(inclusive), _ptr(out)))
+
     # ---- FRI
     def fri_fold(self, evals, out, field, log_n, log_ff, alpha, offset=ONE):
         a = np.ascontiguousarray(alpha, dtype=np.uint64)

@@ -155,8 +155,8 @@ __global__ void __launch_bounds__(128) eval_kernel(const EvalParams p) {
 }
 
 int eval_launch_jit(ms_ctx *c, const uint32_t *program, unsigned nprog, const uint64_t *consts, unsigned nconsts,
-                    const u64 *const *dev_col_ptr, int fq_field, unsigned log_m, uint64_t offset_mont, int trace_bitrev,
-                    int out_bitrev, const u64 *tw_lo, const u64 *tw_hi, u32 hi_len, u64 *out_dev);
+                    const u64 *const *dev_col_ptr, const u64 *dev_consts, int fq_field, unsigned log_m, uint64_t offset_mont,
+                    int trace_bitrev, int out_bitrev, const u64 *tw_lo, const u64 *tw_hi, u32 hi_len, u64 *out_dev);
 
 }  // namespace ms
 
@@ -198,7 +198,7 @@ static int eval_launch(ms_ctx *c, const uint32_t *program, unsigned nprog, const
     // run-time specialised kernel first (eval_jit.cu); the interpreter below is the fallback
     {
         const int jrc = eval_launch_jit(c, program, nprog, consts, nconsts, (const u64 *const *)((char *)meta + prog_bytes + const_bytes),
-                                        fq_field, log_m, offset_mont, trace_bitrev, out_bitrev, tw_lo, tw_hi, hi_len, out_dev);
+                                        (const u64 *)((char *)meta + prog_bytes), fq_field, log_m, offset_mont, trace_bitrev, out_bitrev, tw_lo, tw_hi, hi_len, out_dev);
         if (jrc == MS_OK) return MS_OK;
         if (jrc == MS_ERR_CUDA) return jrc;
     }

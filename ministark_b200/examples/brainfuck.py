@@ -189,6 +189,9 @@ class BrainfuckTrace(Trace):
         base = np.array([[v * _R % P for v in col] for col in zip(*rows)], dtype=np.uint64)
         super().__init__(base, self._extension)
 
+    def build_extension_columns_device(self, challenges, ctx, base_dev):
+        return _device_extension(self, [tuple(c) for c in challenges], ctx, base_dev)
+
     def _extension(self, ch):
         """gen_*_ext_matrix (trace.rs:108-279): running products / evaluations, row by row"""
         rows, n = self.rows, len(self.rows)
@@ -243,6 +246,67 @@ class BrainfuckTrace(Trace):
         for c in range(9):
             out[c] = [w * _R % P for r in range(n) for w in ext[r][c]]
         return out
+
+
+def _device_extension(trace, ch, ctx, base_dev):
+    """The nine extension columns of `BrainfuckTrace._extension`, built on the device: every column is
+    x_0 = init, x_(i+1) = x_i * a_i + b_i  with per-row multipliers / addends that are pointwise expressions of the
+    base row (evaluated by the fused evaluator over the resident trace) — then one parallel scan (ms_scan_affine).
+    Row conditions that look at neighbouring rows or at opcodes are 0/1 helper columns computed from the integer
+    rows on the host (vectorised numpy, a few bytes per row)."""
+    import torch
+    from .. import FP, FQ3, ONE
+    col = lambda c: np.array([r[c] for r in trace.rows], dtype=np.int64)       # small integers (MemValInv is not needed)
+    n = len(trace.rows)
+    log_n = n.bit_length() - 1
+    ci, mv = col(CURR_INSTR), col(MEM_VAL)
+    nxt_mv = np.concatenate([mv[1:], mv[:1]])
+    iip, ici = col(I_IP), col(I_CURR_INSTR)
+    prev_ip = np.concatenate([[-1], iip[:-1]])
+    aux = np.stack([
+        ci != 0,                                               # 0 processor row is not padding
+        ci == READ, (ci == READ) * nxt_mv,                     # 1, 2
+        ci == WRITE, (ci == WRITE) * nxt_mv,                   # 3, 4
+        col(M_DUMMY) == 0,                                     # 5 memory row is real
+        (ici != 0) & (np.arange(n) > 0) & (iip == prev_ip),    # 6 instruction permutation advances
+        iip != prev_ip,                                        # 7 program evaluation advances
+    ]).astype(np.uint64)
+    aux = aux * np.uint64(0xFFFFFFFF)          # Montgomery words: v * (2^64 mod p) needs no reduction for v < 2^32
+    d_aux = torch.from_numpy(aux.view(np.int64)).to(base_dev.device)
+    NB = 17
+    AUX = lambda k: E.Trace(NB + k, 0)
+    T, CH = (lambda c: E.Trace(c, 0)), E.Challenge
+    one = E.Constant(1)
+    instr_fp = lambda ip, c, nx: CH(CH_ALPHA) - CH(CH_A) * ip - CH(CH_B) * c - CH(CH_C) * nx
+    mem_fp = lambda cy, mp, v: CH(CH_BETA) - CH(CH_D) * cy - CH(CH_E) * mp - CH(CH_F) * v
+    gated = lambda mask, factor: one + mask * (factor - one)                      # factor where mask = 1, else 1
+    cols = [base_dev[c] for c in range(NB)] + [d_aux[k] for k in range(aux.shape[0])]
+    is_q = [False] * len(cols)
+    sz = 3 * n
+
+    def evaluate(expr):
+        out = torch.empty(sz, dtype=torch.int64, device=base_dev.device)
+        prog = E.compile_program(expr, len(cols), challenges=ch)
+        ctx.eval_constraints_ptrs(prog, out, log_n, cols, is_q, fq_field=FQ3, offset=ONE)
+        return out
+
+    mont3 = lambda v: np.array([c * _R % P for c in v], dtype=np.uint64)
+    instr_initial, mem_initial = test_rng_fq3(2)
+    zero3 = np.zeros(3, dtype=np.uint64)
+    ext = torch.empty((9, sz), dtype=torch.int64, device=base_dev.device)
+    scan = lambda k, init, **kw: ctx.scan_affine(ext[k], FQ3, n, init, **kw)
+    scan(0, mont3(instr_initial), a=evaluate(gated(AUX(0), instr_fp(T(IP), T(CURR_INSTR), T(NEXT_INSTR)))), a_field=FQ3)
+    scan(1, mont3(mem_initial), a=evaluate(gated(AUX(0), mem_fp(T(CYCLE), T(MP), T(MEM_VAL)))), a_field=FQ3)
+    scan(2, zero3, a=evaluate(gated(AUX(1), CH(CH_GAMMA))), a_field=FQ3, b=d_aux[2], b_field=FP)
+    scan(3, zero3, a=evaluate(gated(AUX(3), CH(CH_DELTA))), a_field=FQ3, b=d_aux[4], b_field=FP)
+    scan(4, mont3(mem_initial), a=evaluate(gated(AUX(5), mem_fp(T(M_CYCLE), T(M_MP), T(M_MEM_VAL)))), a_field=FQ3)
+    scan(5, mont3(instr_initial), a=evaluate(gated(AUX(6), instr_fp(T(I_IP), T(I_CURR_INSTR), T(I_NEXT_INSTR)))), a_field=FQ3,
+         inclusive=True)
+    scan(6, zero3, a=evaluate(gated(AUX(7), CH(CH_ETA))), a_field=FQ3,
+         b=evaluate(AUX(7) * (CH(CH_A) * T(I_IP) + CH(CH_B) * T(I_CURR_INSTR) + CH(CH_C) * T(I_NEXT_INSTR))), b_field=FQ3, inclusive=True)
+    scan(7, zero3, a_const=mont3(ch[CH_GAMMA]), b=base_dev[IN_VALUE], b_field=FP, inclusive=True)
+    scan(8, zero3, a_const=mont3(ch[CH_DELTA]), b=base_dev[OUT_VALUE], b_field=FP, inclusive=True)
+    return ext
 
 
 # ---------------------------------------------------------------- constraints (constraints.rs)

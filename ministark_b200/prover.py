@@ -184,14 +184,18 @@ class GpuProver:
         if tuple(base.shape) != (nbase, n):
             raise ProvingError(f"expected {nbase} base columns of {n} rows")
         base_polys, base_lde, base_tree, base_root = self._commit_columns(base, FP, log_n, log_b, nbase, True)
-        del base
         channel.commit_base_trace(base_root)
         lap("base_trace_commitment")
         challenges = [channel.public_coin.draw() for _ in range(air.num_challenges())]
         hints = air.gen_hints(challenges)
 
         # ---- extension trace commitment (prover.rs:56-72)
-        ext = trace.build_extension_columns(challenges)
+        if hasattr(trace, "build_extension_columns_device"):
+            # running products / evaluations as device scans over the resident base trace
+            ext = trace.build_extension_columns_device(challenges, ctx, base)
+        else:
+            ext = trace.build_extension_columns(challenges)
+        del base
         num_ext = 0 if ext is None else int(ext.shape[0])
         if num_ext != next_:
             raise ProvingError(f"expected {next_} extension columns, got {num_ext}")

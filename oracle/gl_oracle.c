@@ -654,6 +654,20 @@ void orc_divide_out_points(u64 *coeffs, size_t n, const u64 *zs, const u64 *cs, 
         for (unsigned j = 0; j < k; j++) rem[j] = fq3_add(fq3_mul(load_el(zs, 3, j), rem[j]), tmp);
     }
 }
+/* running product / running evaluation columns as the reference builds them row by row
+ * (examples/brainfuck/trace.rs:108-279):  x_0 = init, x_(i+1) = x_i * a_i + b_i;
+ * out[i] = x_i (exclusive: the value stored BEFORE the row's update) or x_(i+1) (inclusive).
+ * a (field fa) NULL => a_i = a_const; b (field fb) NULL => 0; out: n elements of `field`. */
+void orc_scan_affine(unsigned field, const u64 *a, unsigned fa, const u64 *a_const, const u64 *b, unsigned fb, size_t n,
+                     const u64 *init, int inclusive, u64 *out) {
+    fq3 x = load_el(init, 3, 0), ac = a_const ? load_el(a_const, 3, 0) : fq3_one();
+    for (size_t i = 0; i < n; i++) {
+        if (!inclusive) store_el(out, field, i, x);
+        x = fq3_mul(x, a ? load_el(a, fa, i) : ac);
+        if (b) x = fq3_add(x, load_el(b, fb, i));
+        if (inclusive) store_el(out, field, i, x);
+    }
+}
 /* degree adjustment P(x)*(alpha + beta x) (src/composer.rs:167-185), Fq3 coeffs in place */
 void orc_degree_adjust(u64 *coeffs, size_t n, const u64 *alpha, const u64 *beta) {
     fq3 a = load_el(alpha, 3, 0), b = load_el(beta, 3, 0), last = fq3_zero();

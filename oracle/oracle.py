@@ -66,6 +66,7 @@ def lib():
         L.orc_horner.argtypes = [u64p, C.c_uint, C.c_size_t, u64p, u64p]
         L.orc_divide_out_points.argtypes = [u64p, C.c_size_t, u64p, u64p, C.c_uint]
         L.orc_degree_adjust.argtypes = [u64p, C.c_size_t, u64p, u64p]
+        L.orc_scan_affine.argtypes = [C.c_uint, u64p, C.c_uint, u64p, u64p, C.c_uint, C.c_size_t, u64p, C.c_int, u64p]
         L.orc_splitmix_fill.argtypes = [u64p, C.c_size_t, u64]
         L.orc_pow_grind.restype = u64
         L.orc_pow_grind.argtypes = [u8p, C.c_uint]
@@ -233,6 +234,16 @@ def degree_adjust(coeffs, alpha, beta):
     out = np.ascontiguousarray(coeffs).copy()
     lib().orc_degree_adjust(_p(out), out.size // 3, _p(np.ascontiguousarray(alpha, dtype=np.uint64)),
                             _p(np.ascontiguousarray(beta, dtype=np.uint64)))
+    return out
+
+
+def scan_affine(field, n, init, a=None, fa=1, a_const=None, b=None, fb=1, inclusive=False):
+    """x_0 = init, x_(i+1) = x_i * a_i + b_i; returns out[i] = x_i (or x_(i+1) if inclusive), n * field words"""
+    out = np.empty(n * field, dtype=np.uint64)
+    w3 = lambda v: np.ascontiguousarray(v, dtype=np.uint64)
+    lib().orc_scan_affine(field, _p(np.ascontiguousarray(a)) if a is not None else None, fa,
+                          _p(w3(a_const)) if a_const is not None else None,
+                          _p(np.ascontiguousarray(b)) if b is not None else None, fb, n, _p(w3(init)), int(inclusive), _p(out))
     return out
 
 

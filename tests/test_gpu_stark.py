@@ -117,3 +117,19 @@ def test_brainfuck_hello_world_proof_bytes_match_cpu_prover(prover, orc):
     assert got == want
     SO.verify(claim, got, bf.SECURITY_LEVEL, mk)
     assert proof.pow_nonce > 0 and len(proof.fri_proof.layers) == 2
+
+
+def test_brainfuck_extension_columns_on_device_match_host_loops(orc):
+    """§8(f) rank 3: the nine Fq3 running-product / running-evaluation columns from ms_eval_constraints + ms_scan_affine
+    equal the sequential host construction (examples/brainfuck/trace.rs:108-279) word for word"""
+    torch = pytest.importorskip("torch")
+    from ministark_b200.examples import brainfuck as bf
+    ctx = ms.Context(0)
+    for src, inp in ((bf.HELLO_WORLD, b""), (",>,<.>.+[-].", b"hi")):
+        trace, out = bf.simulate(src, inp)
+        ch = [tuple(int(x) for x in np.random.default_rng(k).integers(1, ms.P, size=3, dtype=np.uint64)) for k in range(11)]
+        want = trace.build_extension_columns(ch)
+        base = torch.from_numpy(trace.base_columns().view(np.int64)).cuda()
+        got = trace.build_extension_columns_device(ch, ctx, base)
+        ctx.sync()
+        assert np.array_equal(got.cpu().numpy().view(np.uint64), want)

@@ -227,3 +227,21 @@ def test_pow_grind_vs_hashlib(orc):
             return len(bin(int.from_bytes(d, "big"))) - 2 if False else 256 - int.from_bytes(d, "big").bit_length()
         assert nonce >= 1 and lz(nonce) >= bits
         assert all(lz(k) < bits for k in range(1, nonce))
+
+
+def test_scan_affine_oracle_vs_definition(orc):
+    # x_0 = init, x_(i+1) = x_i * a_i + b_i in big-int Python
+    n = 37
+    a = orc.rand_matrix(1, n, 3, seed=5)[0]
+    b = orc.rand_matrix(1, n, 1, seed=6)[0]
+    init = orc.rand_matrix(1, 1, 3, seed=7)[0]
+    x = tuple(S.from_mont(int(w)) for w in init)
+    want_ex, want_in = [], []
+    for i in range(n):
+        want_ex.append(x)
+        ai = tuple(S.from_mont(int(w)) for w in a[3 * i:3 * i + 3])
+        x = S.fq3_add(S.fq3_mul(x, ai), (S.from_mont(int(b[i])), 0, 0))
+        want_in.append(x)
+    canon = lambda arr: [tuple(S.from_mont(int(w)) for w in arr[3 * i:3 * i + 3]) for i in range(n)]
+    assert canon(orc.scan_affine(3, n, init, a=a, fa=3, b=b, fb=1, inclusive=False)) == want_ex
+    assert canon(orc.scan_affine(3, n, init, a=a, fa=3, b=b, fb=1, inclusive=True)) == want_in
