@@ -181,7 +181,7 @@ def full_prove_sample(log_rows=21):
     from ministark_b200.examples import fib
     from ministark_b200.prover import GpuProver
     from oracle import stark_oracle
-    trace, last = fib.gen_trace(8 << log_rows)
+    trace, last = fib.gen_trace(8 << log_rows, pinned=True)      # page-locked columns, like the reference's GpuAllocator
     claim = fib.FibClaim(last)
     prover = GpuProver(0)
     prover.prove(claim, fib.OPTIONS, trace)
@@ -194,7 +194,7 @@ def full_prove_sample(log_rows=21):
     dt, proof = best
     pb = proof.to_bytes()
     stark_oracle.verify(claim, pb, fib.SECURITY_LEVEL, lambda n, o: Air(claim.AirConfig, n, claim.get_public_inputs(), ProofOptions(*o)))
-    return {"workload": f"examples/fib: 2^{log_rows} rows x 8 Fp columns, ProofOptions(32, 4, 8, 8, 64), host trace -> proof",
+    return {"workload": f"examples/fib: 2^{log_rows} rows x 8 Fp columns, ProofOptions(32, 4, 8, 8, 64), pinned host trace -> proof",
             "seconds": dt, "phases_s": {k: round(v, 5) for k, v in proof.timings.items()}, "proof_bytes": len(pb),
             "verified": True, "launches": prover.ctx.launches}
 

@@ -8,7 +8,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libministark_b200.so")
+LIB_PATH = os.environ.get("MS_LIB_PATH") or os.path.join(_HERE, "libministark_b200.so")   # MS_LIB_PATH: A/B builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ministark_b200.h")
 
 u64 = C.c_uint64

@@ -55,9 +55,11 @@ class FibAirConfig(AirConfig):
         return boundary + terminal + transition
 
 
-def gen_trace(n):
+def gen_trace(n, pinned=False):
     """n = total number of sequence values; the trace has n / 8 rows of 8 consecutive values (main.rs:175-222).
-    v_0 = 1, v_1 = 2, v_k = v_(k-2) * v_(k-1).  Returns (Trace, last value of column 7 as a canonical int)."""
+    v_0 = 1, v_1 = 2, v_k = v_(k-2) * v_(k-1).  Returns (Trace, last value of column 7 as a canonical int).
+    pinned: put the columns in page-locked host memory (the reference allocates them with GpuAllocator, main.rs:181-188)
+    so that the prover's chunked upload overlaps with the transforms."""
     assert n & (n - 1) == 0 and n > 8
     num_rows = n // 8
     # v_k = 2^F(k) and 2 has order 192 in Goldilocks, so the sequence is periodic (period 96 = Pisano(192));
@@ -78,6 +80,11 @@ def gen_trace(n):
     reps = -(-num_rows // len(rows))
     cols = np.ascontiguousarray(np.tile(period, (reps, 1))[:num_rows].T)
     last = rows[(num_rows - 1) % len(rows)][7]
+    if pinned:
+        import torch
+        host = torch.empty((8, num_rows), dtype=torch.int64, pin_memory=True)
+        host.numpy().view(np.uint64)[:] = cols
+        return Trace(host), last
     return Trace(cols), last
 
 

@@ -118,6 +118,7 @@ class GpuProver:
     def __init__(self, device=0):
         self.device = torch.device("cuda", device)
         self.stream = torch.cuda.Stream(device=self.device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
         self.ctx = Context(device, stream=self.stream.cuda_stream)
 
     # ---- helpers
@@ -179,11 +180,36 @@ class GpuProver:
         nbase, next_ = cfg.NUM_BASE_COLUMNS, cfg.NUM_EXTENSION_COLUMNS
         lap("init_air")
 
-        # ---- base trace commitment (prover.rs:46-55)
-        base = self._to_device(trace.base_columns())
-        if tuple(base.shape) != (nbase, n):
+        # ---- base trace commitment (prover.rs:46-55).  A host trace is uploaded in column chunks on a second stream
+        # while the previous chunk is interpolated and extended (columns are independent until the row hash); a
+        # pinned trace — the analogue of the reference's GpuAllocator-backed columns — makes the copies asynchronous.
+        host_base = trace.base_columns()
+        if tuple(host_base.shape) != (nbase, n):
             raise ProvingError(f"expected {nbase} base columns of {n} rows")
-        base_polys, base_lde, base_tree, base_root = self._commit_columns(base, FP, log_n, log_b, nbase, True)
+        if isinstance(host_base, torch.Tensor) and host_base.is_cuda:
+            base = host_base.to(self.device)
+            base_polys, base_lde, base_tree, base_root = self._commit_columns(base, FP, log_n, log_b, nbase, True)
+        else:
+            if not isinstance(host_base, torch.Tensor):
+                host_base = torch.from_numpy(np.ascontiguousarray(host_base, dtype=np.uint64).view(np.int64))
+            base, base_polys, base_lde = self._empty(nbase, n), self._empty(nbase, n), self._empty(nbase, N)
+            chunk = max(1, min(nbase, (64 << 20) // (8 * n) or 1))            # ~64 MiB per copy
+            self.copy_stream.wait_stream(self.stream)
+            events = []
+            with torch.cuda.stream(self.copy_stream):
+                for c0 in range(0, nbase, chunk):
+                    c1 = min(c0 + chunk, nbase)
+                    base[c0:c1].copy_(host_base[c0:c1], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self.copy_stream)
+                    events.append((c0, c1, ev))
+            for c0, c1, ev in events:
+                self.stream.wait_event(ev)
+                ctx.ntt_batch_to(base[c0], base_polys[c0], FP, log_n, c1 - c0, inverse=True)
+                ctx.lde_batch(base_polys[c0], base_lde[c0], FP, log_n, log_b, c1 - c0, offset=GEN_MONT, bitrev=True)
+            leaves, nodes = self._empty(N, 4), self._empty(N, 4)
+            base_root = ctx.merkle_commit(base_lde, FP, N, nbase, leaves=leaves, nodes=nodes)
+            base_tree = _Tree(leaves, nodes, N)
         channel.commit_base_trace(base_root)
         lap("base_trace_commitment")
         challenges = [channel.public_coin.draw() for _ in range(air.num_challenges())]
