@@ -197,6 +197,10 @@ int ms_eval_constraints_ptrs(ms_ctx *ctx, const uint32_t *program, unsigned npro
                              int fq_field, unsigned log_m, uint64_t offset_mont, int trace_bitrev, int out_bitrev,
                              void *out);
 
+/* diagnostic (tests only): the lazy field primitives of the NTT butterflies, element-wise over ANY 64-bit words:
+ * out[k*n + i], k = 0 add_lc(a, canon b), 1 sub_lc(a, canon b), 2 add_ll(a, b), 3 sub_ll(a, b), 4 mul(a, canon b) */
+int ms_debug_lazy_ops(ms_ctx *ctx, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out);
+
 /* diagnostic, needs no GPU: generate the run-time specialised evaluation kernel for a program (csrc/eval_jit.cu)
  * and compile it with NVRTC for sm_100a.  0 = ok, 1 = NVRTC not installed (the interpreter kernel is used),
  * -1 = compile error (log_out receives the NVRTC log) */

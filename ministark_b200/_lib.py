@@ -49,6 +49,7 @@ _SIGS = {
     "ms_matrix_from_rows": (ci, [vp, ci, vp, sz, ui, vp, sz]),
     "ms_gather_rows": (ci, [vp, ci, vp, sz, ui, sz, vp, ui, vp]),
     "ms_gather_rows_rowmajor": (ci, [vp, vp, ui, sz, vp, ui, vp]),
+    "ms_debug_lazy_ops": (ci, [vp, vp, vp, sz, vp]),
     "ms_scan_affine": (ci, [vp, ci, vp, ci, vp, vp, ci, sz, vp, ci, vp]),
     "ms_fri_fold": (ci, [vp, ci, vp, ui, ui, u64, vp, vp]),
     "ms_eval_constraints": (ci, [vp, vp, ui, vp, ui, vp, sz, ui, vp, sz, ui, ci, ui, u64, ci, ci, vp]),

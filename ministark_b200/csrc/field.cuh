@@ -80,12 +80,17 @@ __device__ __forceinline__ u64 sub_lc(u64 a, u64 t) {
         : "=r"(s0), "=r"(s1) : "r"(a0), "r"(a1), "r"(t0), "r"(t1));
     return pack64(s0, s1);
 }
+// Both repairs are exact 64-bit additions of eps = (0 : 0xffffffff) gated by the previous carry (m = -carry), so the
+// carry of each repair is the true carry — including a + t == 2^64 exactly, where the first sum is 0 (an earlier
+// version repaired with "low -= c, high -= borrow, high += c" and took the carry of the last add, which is spurious
+// in exactly that case: found by the brainfuck MemValInv column, whose words 2^63 + 2^63 sum to 2^64).
+// (PTX carry flags follow the hardware: after add.cc CF is the carry, after sub.cc it is NOT borrow.)
 __device__ __forceinline__ u64 add_ll(u64 a, u64 t) {
     u32 a0, a1, t0, t1, s0, s1;
     unpack64(a, a0, a1); unpack64(t, t0, t1);
-    asm("{\n\t.reg .u32 c;\n\tadd.cc.u32 %0, %2, %4;\n\taddc.cc.u32 %1, %3, %5;\n\taddc.u32 c, 0, 0;\n\t"
-        "sub.cc.u32 %0, %0, c;\n\tsubc.u32 %1, %1, 0;\n\tadd.cc.u32 %1, %1, c;\n\taddc.u32 c, 0, 0;\n\t"
-        "sub.cc.u32 %0, %0, c;\n\tsubc.u32 %1, %1, 0;\n\tadd.u32 %1, %1, c;\n\t}"
+    asm("{\n\t.reg .u32 c, m;\n\tadd.cc.u32 %0, %2, %4;\n\taddc.cc.u32 %1, %3, %5;\n\taddc.u32 c, 0, 0;\n\tsub.u32 m, 0, c;\n\t"
+        "add.cc.u32 %0, %0, m;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.u32 c, 0, 0;\n\tsub.u32 m, 0, c;\n\t"
+        "add.cc.u32 %0, %0, m;\n\taddc.u32 %1, %1, 0;\n\t}"
         : "=r"(s0), "=r"(s1) : "r"(a0), "r"(a1), "r"(t0), "r"(t1));
     return pack64(s0, s1);
 }

@@ -130,6 +130,18 @@ __global__ void gather_rows_kernel(const u64 *cols, size_t col_stride_words, uns
     for (unsigned w = 0; w < ew; w++) out[((size_t)q * ncols + cc) * ew + w] = cols[(size_t)cc * col_stride_words + rows[q] * ew + w];
 }
 
+// diagnostic: the lazy field primitives the NTT butterflies are built from, applied element-wise (tests only)
+__global__ void lazy_ops_kernel(const u64 *a, const u64 *b, size_t n, u64 *out) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 x = a[i], y = b[i], yc = gl::canon(y);
+    out[i] = gl::add_lc(x, yc);
+    out[n + i] = gl::sub_lc(x, yc);
+    out[2 * n + i] = gl::add_ll(x, y);
+    out[3 * n + i] = gl::sub_ll(x, y);
+    out[4 * n + i] = gl::mul(x, yc);
+}
+
 }  // namespace ms
 
 using namespace ms;
@@ -308,6 +320,27 @@ int ms_gather_rows_rowmajor(ms_ctx *c, const void *rows, unsigned row_words, siz
     MS_CUDA(c, cudaStreamSynchronize(c->stream));
     if ((rc = in.finish())) return rc;
     return o.finish();
+}
+
+// Diagnostic (tests only): out[k*n + i] = op_k(a[i], b[i]) for the lazy primitives of field.cuh — k = 0 add_lc(a, canon b),
+// 1 sub_lc(a, canon b), 2 add_ll(a, b), 3 sub_ll(a, b), 4 mul(a, canon b).  a, b: ANY 64-bit words.  Results of 0..3 are
+// lazy (any u64 congruent to the exact result mod p); mul is canonical.
+int ms_debug_lazy_ops(ms_ctx *c, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out) {
+    if (!c || !a || !b || !out) return MS_ERR_INVALID;
+    if (n == 0) return MS_OK;
+    Staged A(c, a, n * 8, true, false);
+    if (A.rc) return A.rc;
+    Staged B(c, b, n * 8, true, false);
+    if (B.rc) return B.rc;
+    Staged O(c, out, 5 * n * 8, false, true);
+    if (O.rc) return O.rc;
+    lazy_ops_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(A.as<u64>(), B.as<u64>(), n, O.as<u64>());
+    c->launches++;
+    MS_CHECK_LAUNCH(c);
+    int rc;
+    if ((rc = A.finish())) return rc;
+    if ((rc = B.finish())) return rc;
+    return O.finish();
 }
 
 }  // extern "C"

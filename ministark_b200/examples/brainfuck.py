@@ -30,6 +30,15 @@ OPTIONS = ProofOptions(19, 16, 20, 16, 16)          # main.rs:92-105, 96-bit sec
 SECURITY_LEVEL = 96
 
 HELLO_WORLD = ("++++++++++[>+++++++>++++++++++>+++>+<<<<-]>++.>+.+++++++..+++.>++.<<+++++++++++++++.>.+++.------.--------.")
+
+
+def cycle_burner(a, b, c):
+    """a * b * (3c + 5) + O(a) cycles in three nested count-down loops; no cell ever exceeds max(a, b, c), so the
+    u8 tape never wraps (a wrap would violate the MemVal transition constraints)."""
+    assert max(a, b, c) < 256
+    return "+" * a + "[>" + "+" * b + "[>" + "+" * c + "[-]<-]<-]"
+
+
 OPCODES = [ord(c) for c in "><+-.,[]"]               # OpCode::VALUES order (vm.rs:23-33)
 INC_PTR, DEC_PTR, INC, DEC, WRITE, READ, LOOP_BEGIN, LOOP_END = OPCODES
 
@@ -108,12 +117,13 @@ def simulate(source, input_bytes=b""):
     # derive_memory_rows (vm.rs:338-381)
     mem = [[r[CYCLE], r[MP], r[MEM_VAL], 0] for r in proc if r[CURR_INSTR] != 0]
     mem.sort(key=lambda r: (r[1], r[0]))
-    i = 0
-    while i < len(mem) - 1:
-        c, n = mem[i], mem[i + 1]
-        if c[1] == n[1] and c[0] + 1 != n[0]:
-            mem.insert(i + 1, [c[0] + 1, c[1], c[2], 1])
-        i += 1
+    # dummy rows so that the cycle count never jumps within one address (the reference inserts them one at a time)
+    filled = []
+    for k, c in enumerate(mem):
+        filled.append(c)
+        if k + 1 < len(mem) and c[1] == mem[k + 1][1]:
+            filled.extend([cy, c[1], c[2], 1] for cy in range(c[0] + 1, mem[k + 1][0]))
+    mem = filled
     longest = max(len(proc), len(mem), len(instr), len(in_rows), len(out_rows))
     n = longest if longest & (longest - 1) == 0 else 1 << longest.bit_length()
     while len(proc) < n:
@@ -186,7 +196,13 @@ def _sub_scaled(acc, ch, v):
 class BrainfuckTrace(Trace):
     def __init__(self, rows):
         self.rows = rows
-        base = np.array([[v * _R % P for v in col] for col in zip(*rows)], dtype=np.uint64)
+        # every entry is a small integer except MemValInv = 1 / mem_val with mem_val < 256: Montgomery words are
+        # v * (2^64 mod p) = v * (2^32 - 1) (no reduction needed below 2^32) and a 256-entry table of inverses
+        ints = np.array([[0 if c == MEM_VAL_INV else v for c, v in enumerate(r)] for r in rows], dtype=np.uint64).T
+        self.int_cols = np.ascontiguousarray(ints).astype(np.int64)
+        base = np.ascontiguousarray(ints * np.uint64(0xFFFFFFFF))
+        inv_lut = np.array([0] + [pow(v, -1, P) * _R % P for v in range(1, 256)], dtype=np.uint64)
+        base[MEM_VAL_INV] = inv_lut[ints[MEM_VAL]]
         super().__init__(base, self._extension)
 
     def build_extension_columns_device(self, challenges, ctx, base_dev):
@@ -256,7 +272,7 @@ def _device_extension(trace, ch, ctx, base_dev):
     rows on the host (vectorised numpy, a few bytes per row)."""
     import torch
     from .. import FP, FQ3, ONE
-    col = lambda c: np.array([r[c] for r in trace.rows], dtype=np.int64)       # small integers (MemValInv is not needed)
+    col = lambda c: trace.int_cols[c]                                        # small integers (MemValInv is not needed)
     n = len(trace.rows)
     log_n = n.bit_length() - 1
     ci, mv = col(CURR_INSTR), col(MEM_VAL)

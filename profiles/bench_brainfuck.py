@@ -13,6 +13,33 @@ from ministark_b200.prover import GpuProver
 from oracle import oracle as orc
 from oracle import stark_oracle as SO
 
+if len(sys.argv) > 1 and sys.argv[1] == "--burner":
+    # a large brainfuck trace: GPU prove + restated verifier only (the CPU prover would need tens of minutes)
+    a, b, c = (int(v) for v in sys.argv[2:5])
+    src = bf.cycle_burner(a, b, c)
+    t = time.perf_counter()
+    trace, out = bf.simulate(src)
+    t_sim = time.perf_counter() - t
+    claim = bf.BrainfuckClaim(src, b"", out)
+    mk = lambda n, o: Air(claim.AirConfig, n, claim, ProofOptions(*o))
+    prover = GpuProver(0)
+    prover.prove(claim, bf.OPTIONS, trace)
+    best = None
+    for _ in range(2):
+        t = time.perf_counter()
+        proof = prover.prove(claim, bf.OPTIONS, trace)
+        dt = time.perf_counter() - t
+        best = (dt, proof) if best is None or dt < best[0] else best
+    dt, proof = best
+    pb = proof.to_bytes()
+    t = time.perf_counter()
+    SO.verify(claim, pb, bf.SECURITY_LEVEL, mk)
+    print(json.dumps({"bench": "brainfuck_cycle_burner", "program": f"cycle_burner({a},{b},{c})", "rows": len(trace),
+                      "cols": "17 Fp + 9 Fq3", "options": [19, 16, 20, 16, 16], "simulate_s_python_vm": t_sim, "gpu_prove_s": dt,
+                      "phases_s": {k: round(v, 5) for k, v in proof.timings.items()}, "proof_bytes": len(pb),
+                      "verify_s": time.perf_counter() - t, "verified": True, "launches": prover.ctx.launches}))
+    sys.exit(0)
+
 t = time.perf_counter()
 trace, out = bf.simulate(bf.HELLO_WORLD)
 t_sim = time.perf_counter() - t

@@ -95,6 +95,19 @@ def test_lde_fp(ctx, orc, log_n, log_b, bitrev):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("log_n,log_b,ncols", [(10, 4, 17), (10, 4, 3), (10, 3, 17), (8, 4, 5), (6, 4, 9), (10, 4, 1), (9, 4, 17),
+                                                 (11, 4, 17), (12, 4, 17), (7, 5, 33), (10, 2, 26), (13, 4, 17)])
+def test_lde_and_interpolate_many_columns_small_sizes(ctx, orc, log_n, log_b, ncols):
+    # shapes the full prover produces (e.g. brainfuck: 17 base columns, n = 2^10, blow-up 16)
+    trace = orc.rand_matrix(ncols, 1 << log_n, 1, seed=31 * log_n + ncols)
+    m = ms.Matrix(trace, ms.FP, ctx)
+    polys = m.interpolate(ms.Domain(log_n))
+    want_polys = orc.ntt(trace, 1, log_n, inverse=True)
+    assert np.array_equal(polys.cols, want_polys)
+    got = polys.bit_reversed_evaluate(ms.Domain(log_n + log_b, ms.GENERATOR)).cols
+    assert np.array_equal(got, orc.lde(want_polys, 1, log_n, log_b, orc.generator(), bitrev=True))
+
+
 @pytest.mark.parametrize("log_n,log_b", [(4, 2), (11, 4), (13, 3)])
 def test_lde_fq3(ctx, orc, log_n, log_b):
     coeffs = orc.rand_matrix(2, 1 << log_n, 3, seed=log_n)
@@ -167,3 +180,77 @@ def test_large_sizes_by_properties(ctx, orc):
         x = orc.fp_mul(orc.generator(), orc.fp_pow(g, i))
         pt = np.array([x, 0, 0], dtype=np.uint64)
         assert int(orc.horner(coeffs, 1, pt)[0]) == int(ev[i])
+
+
+# ---- edge arithmetic: the lazy primitives and structured (non-random) columns ---------------------------------------
+_EDGE = [0, 1, 2, 3, 2**31, 2**32 - 2, 2**32 - 1, 2**32, 2**32 + 1, 2**33 - 2, 2**33 - 1, 2**33, 2**62, 2**63 - 1, 2**63, 2**63 + 1,
+         2**63 + 2**31, 2**64 - 2**33, 2**64 - 2**32 - 1, ms.P - 2, ms.P - 1, ms.P, ms.P + 1, ms.P + 2**32 - 2, 2**64 - 2**32 + 2**31,
+         2**64 - 2**31, 2**64 - 2, 2**64 - 1, 0xFFFFFFFF00000000, 0x00000000FFFFFFFF, 0x8000000080000000, 0x7FFFFFFFFFFFFFFF,
+         0xFFFFFFFEFFFFFFFF, 0xFFFFFFFF7FFFFFFF, 0x0000000100000000, 0x00000001FFFFFFFF, 0xAAAAAAAAAAAAAAAA, 0x5555555555555555]
+
+
+def test_lazy_primitives_all_edge_pairs(ctx):
+    """add_lc / sub_lc / add_ll / sub_ll / mul of csrc/field.cuh on every pair of edge words (incl. a + b == 2^64 exactly,
+    a == b, operands >= p) plus random pairs, against big-integer arithmetic mod p"""
+    import ctypes as C
+    rng = np.random.default_rng(1)
+    a = np.array([x for x in _EDGE for _ in _EDGE] + list(rng.integers(0, 2**64, size=4096, dtype=np.uint64)), dtype=np.uint64)
+    b = np.array([y for _ in _EDGE for y in _EDGE] + list(rng.integers(0, 2**64, size=4096, dtype=np.uint64)), dtype=np.uint64)
+    # pairs that sum to exactly 2^64 and pairs that differ by exactly eps / p
+    extra = [(x, (2**64 - x) % 2**64) for x in _EDGE if x] + [(x, (x + 2**32 - 1) % 2**64) for x in _EDGE] + [(x, (x + ms.P) % 2**64) for x in _EDGE]
+    a = np.concatenate([a, np.array([e[0] for e in extra], dtype=np.uint64)])
+    b = np.concatenate([b, np.array([e[1] for e in extra], dtype=np.uint64)])
+    n = a.size
+    out = np.empty(5 * n, dtype=np.uint64)
+    ctx._ck(ctx.lib.ms_debug_lazy_ops(ctx.h, a.ctypes.data, b.ctypes.data, n, out.ctypes.data))
+    out = out.reshape(5, n)
+    P, RINV = ms.P, pow(2**64, -1, ms.P)
+    for i in range(n):
+        x, y = int(a[i]), int(b[i])
+        yc = y - P if y >= P else y
+        assert int(out[0, i]) % P == (x + yc) % P, ("add_lc", hex(x), hex(y))
+        assert int(out[1, i]) % P == (x - yc) % P, ("sub_lc", hex(x), hex(y))
+        assert int(out[2, i]) % P == (x + y) % P, ("add_ll", hex(x), hex(y))
+        assert int(out[3, i]) % P == (x - y) % P, ("sub_ll", hex(x), hex(y))
+        assert int(out[4, i]) == x * yc * RINV % P, ("mul", hex(x), hex(y))
+
+
+def _structured_columns(n, rng):
+    """columns a real execution trace has: constants, 0/1 flags, counters, a handful of repeated values such as the
+    Montgomery words of 1/2 = 2^63 and 1/4 = 2^62 (their pairwise sums hit 2^64 exactly), runs, alternations"""
+    R, P = 2**64, ms.P
+    mont = lambda v: np.array([int(x) * R % P for x in v], dtype=np.uint64)
+    inv = [0] + [pow(v, -1, P) for v in range(1, 9)]
+    cols = [
+        np.zeros(n, dtype=np.uint64), np.full(n, ms.ONE, dtype=np.uint64), np.full(n, 2**63, dtype=np.uint64), np.full(n, P - 1, dtype=np.uint64),
+        mont(np.arange(n) % 2), mont(np.arange(n)), mont([inv[int(k)] for k in rng.integers(0, 5, size=n)]),
+        mont([inv[(i // 3) % 9] for i in range(n)]), np.where(np.arange(n) % 2 == 0, np.uint64(2**63), np.uint64(2**62)),
+        np.where(np.arange(n) < n // 2, np.uint64(2**63), np.uint64(0)), mont([P - 1 - (i % 4) for i in range(n)]),
+        np.where(rng.integers(0, 2, size=n) == 0, np.uint64(2**63), np.uint64(P - 2**63)),
+    ]
+    return np.stack(cols)
+
+
+@pytest.mark.parametrize("log_n", list(range(1, 17)))
+def test_structured_columns_all_transforms(ctx, orc, log_n):
+    """forward / inverse, subgroup / coset NTT and the coset LDE on structured columns (the brainfuck MemValInv column —
+    values 0, 1, 1/2, 1/3, 1/4 — exposed a spurious second carry in add_ll when two words sum to exactly 2^64)"""
+    rng = np.random.default_rng(log_n)
+    n = 1 << log_n
+    cols = _structured_columns(n, rng)
+    k = cols.shape[0]
+    for inverse in (False, True):
+        for offset in (orc.ONE, orc.generator()):
+            got = cols.copy()
+            ctx.ntt_batch(got, ms.FP, log_n, k, inverse=inverse, offset=offset)
+            assert np.array_equal(got, orc.ntt(cols, 1, log_n, offset, inverse=inverse)), (inverse, offset)
+    polys = orc.ntt(cols, 1, log_n, inverse=True)
+    for log_b in (1, 4):
+        out = np.empty((k, n << log_b), dtype=np.uint64)
+        ctx.lde_batch(polys, out, ms.FP, log_n, log_b, k, offset=ms.GENERATOR, bitrev=True)
+        assert np.array_equal(out, orc.lde(polys, 1, log_n, log_b, orc.generator(), bitrev=True)), log_b
+    # Fq3: the three lanes of a structured extension column
+    q = np.ascontiguousarray(np.stack([cols[6], cols[2], cols[8]], axis=1).reshape(1, 3 * n))
+    got = q.copy()
+    ctx.ntt_batch(got, ms.FQ3, log_n, 1, inverse=True)
+    assert np.array_equal(got, orc.ntt(q, 3, log_n, inverse=True))

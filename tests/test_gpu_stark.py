@@ -133,3 +133,20 @@ def test_brainfuck_extension_columns_on_device_match_host_loops(orc):
         got = trace.build_extension_columns_device(ch, ctx, base)
         ctx.sync()
         assert np.array_equal(got.cpu().numpy().view(np.uint64), want)
+
+
+def test_brainfuck_cycle_burner_proof_bytes_match_cpu_prover(prover, orc):
+    """a loop-heavy program (1024 rows): exercises LoopBegin / LoopEnd jumps, dummy memory rows and the device-built
+    extension columns inside the full prover"""
+    from oracle import stark_oracle as SO
+    from ministark_b200.examples import brainfuck as bf
+    src = bf.cycle_burner(4, 4, 4)
+    trace, out = bf.simulate(src)
+    assert len(trace) == 1024
+    claim = bf.BrainfuckClaim(src, b"", out)
+    mk = lambda n, o: Air(claim.AirConfig, n, claim, ProofOptions(*o))
+    opts = (16, 16, 6, 8, 8)
+    got = prover.prove(claim, ProofOptions(*opts), trace).to_bytes()
+    want = SO.cpu_prove(claim, opts, trace.base_columns(), mk, ext_builder=trace.build_extension_columns)
+    assert got == want
+    SO.verify(claim, got, 60, mk)
