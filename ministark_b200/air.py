@@ -187,6 +187,26 @@ class Air:
     def lde_blowup_factor(self):
         return self.options.lde_blowup_factor
 
+    # ---- compiled evaluator programs, shared by every proof of this AIR and trace length (the verifier randomness
+    # enters through Program.bind, not through the instruction stream)
+    def composition_program(self):
+        if getattr(self, "_composition_program", None) is None:
+            cfg = self.config
+            log_ce = self.log_n + self.ce_blowup_factor.bit_length() - 1
+            self._composition_program = E.compile_program(self.composition_constraint, cfg.NUM_BASE_COLUMNS,
+                                                          lde_step=self.ce_blowup_factor, log_ce=log_ce, symbolic=True)
+        return self._composition_program
+
+    def deep_program(self):
+        if getattr(self, "_deep_program", None) is None:
+            from . import deep
+            cfg = self.config
+            log_N = self.log_n + self.options.lde_blowup_factor.bit_length() - 1
+            expr, keys = deep.deep_expression_symbolic(self.trace_arguments(), cfg.NUM_BASE_COLUMNS, cfg.NUM_EXTENSION_COLUMNS,
+                                                       self.ce_blowup_factor)
+            self._deep_program = (E.compile_program(expr, cfg.NUM_BASE_COLUMNS, log_ce=log_N, symbolic=True), keys)
+        return self._deep_program
+
     def num_challenges(self):
         idx = [a[0] for c in self.constraints for a in _leaves(c, "chal")]
         return max(idx) + 1 if idx else 0

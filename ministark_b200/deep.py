@@ -60,3 +60,41 @@ def deep_expression(trace_arguments, num_base_cols, num_ext_cols, num_compositio
         term = (E.Trace(col, 0) - E.Constant(ood)) * inv_x_minus(tuple(z_points[off])) * E.Constant(alpha)
         total = term if total is None else total + term
     return total * (E.Constant(degree_alpha) + x * E.Constant(degree_beta))
+
+
+def deep_expression_symbolic(trace_arguments, num_base_cols, num_ext_cols, num_composition_cols):
+    """The same expression with every per-proof value (out-of-domain points and values, alphas, degree coefficients)
+    as a Hint placeholder, so that it is compiled ONCE per AIR (expr.compile_program(..., symbolic=True)) and bound per
+    proof (Program.bind(hints=deep_hint_values(...))).  Returns (expr, keys); keys[i] names hint i."""
+    keys, index = [], {}
+
+    def H(key):
+        if key not in index:
+            index[key] = len(keys)
+            keys.append(key)
+        return E.Hint(index[key])
+
+    x = E.X()
+    inv_cache = {}
+
+    def inv_x_minus(key):
+        if key not in inv_cache:
+            inv_cache[key] = E.Constant(1) / (x - H(key))
+        return inv_cache[key]
+
+    total = None
+    ncols_trace = num_base_cols + num_ext_cols
+    for j in range(num_composition_cols):
+        term = (E.Trace(ncols_trace + j, 0) - H(("cood", j))) * inv_x_minus(("zm",)) * H(("calpha", j))
+        total = term if total is None else total + term
+    for i, (col, off) in enumerate(trace_arguments):
+        term = (E.Trace(col, 0) - H(("tood", i))) * inv_x_minus(("zpt", off)) * H(("talpha", i))
+        total = term if total is None else total + term
+    return total * (H(("dalpha",)) + x * H(("dbeta",))), keys
+
+
+def deep_hint_values(keys, z_points, z_m, trace_oods, composition_oods, trace_alphas, composition_alphas, degree_alpha, degree_beta):
+    table = {"zm": lambda: z_m, "dalpha": lambda: degree_alpha, "dbeta": lambda: degree_beta,
+             "zpt": lambda off: z_points[off], "tood": lambda i: trace_oods[i], "cood": lambda j: composition_oods[j],
+             "talpha": lambda i: trace_alphas[i], "calpha": lambda j: composition_alphas[j]}
+    return [tuple(table[k[0]](*k[1:])) for k in keys]

@@ -139,17 +139,34 @@ def Trace(col, offset=0):
 
 
 class Program:
-    def __init__(self, code, consts, nregs, out_is_q):
+    def __init__(self, code, consts, nregs, out_is_q, bindings=()):
         self.code = np.ascontiguousarray(code, dtype=np.uint32).reshape(-1, 4)
         self.consts = np.ascontiguousarray(consts, dtype=np.uint64).reshape(-1, 3)
         self.nregs, self.out_is_q = nregs, out_is_q
+        self.bindings = list(bindings)          # (constant slot, "chal" | "hint" | "ccoef", index): filled by bind()
+
+    def bind(self, challenges=(), hints=(), ccoefs=()):
+        """a copy of this program whose symbolic constants hold this proof's verifier randomness.  The instruction
+        stream — and with it the run-time specialised kernel (csrc/eval_jit.cu keys on the code only) — is shared by
+        every proof of the same AIR and trace length; only this small table changes."""
+        src = {"chal": challenges, "hint": hints, "ccoef": ccoefs}
+        consts = self.consts.copy()
+        for slot, kind, idx in self.bindings:
+            consts[slot] = [c * _R % P for c in _q(src[kind][idx])]
+        return Program(self.code, consts, self.nregs, self.out_is_q)
 
     def __len__(self):
         return self.code.shape[0]
 
 
-def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, log_ce=None, fold_pow0=True):
+_SYMBOLIC = ("chal", "hint", "ccoef")
+
+
+def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, log_ce=None, fold_pow0=True, symbolic=False):
     """Flatten `expr` into the evaluator's linear program.
+
+    symbolic=True keeps Challenge / Hint / CompositionCoeff leaves as run-time constants (Program.bind fills them in)
+    instead of folding their values into the program: compile once per AIR, bind per proof.
 
     challenges / hints: extension elements as 3-tuples (or ints) of canonical integers, substituted
     as constants exactly like eval_cpu.rs:116-118.  Trace(col, off) with col < num_base_cols reads a
@@ -220,6 +237,8 @@ def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, lo
         if k == "const":
             cval[id(nd)] = a[0]
             typ[id(nd)] = FQ if a[1] else FP
+        elif k in _SYMBOLIC and symbolic:
+            typ[id(nd)] = FQ
         elif k == "chal":
             cval[id(nd)] = _q(challenges[a[0]])
             typ[id(nd)] = FQ
@@ -266,8 +285,10 @@ def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, lo
     # trace cells from dozens of constraints).  Interior temporaries are never evicted.
     leaf_regs, pinned, touch = {}, set(), {}
 
+    bindings, sym_slot = [], {}
+
     def is_leaf(x):
-        return id(x) in cval or x.kind in ("x", "trace")
+        return id(x) in cval or x.kind in ("x", "trace") or x.kind in _SYMBOLIC
 
     def alloc():
         nonlocal nregs
@@ -287,6 +308,13 @@ def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, lo
         r = alloc()
         if id(x) in cval:
             code.append([OP_CONST | (typ[id(x)] << 8), r, const_slot(cval[id(x)]), 0])
+        elif x.kind in _SYMBOLIC:
+            key = (x.kind, x.args[0])
+            if key not in sym_slot:
+                sym_slot[key] = len(consts)
+                consts.append([0, 0, 0])
+                bindings.append((sym_slot[key], x.kind, x.args[0]))
+            code.append([OP_CONST | (FQ << 8), r, sym_slot[key], 0])
         elif x.kind == "x":
             code.append([OP_X, r, 0, 0])
         else:
@@ -347,4 +375,4 @@ def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, lo
         reg_of[id(nd)] = r
     code.append([OP_STORE | (typ[id(expr)] << 8), 0, reg_of[id(expr)], 0])
     return Program(np.array(code, dtype=np.uint32), np.array(consts if consts else [[0, 0, 0]], dtype=np.uint64),
-                   max(nregs, 1), typ[id(expr)] == FQ)
+                   max(nregs, 1), typ[id(expr)] == FQ, bindings)

@@ -19,6 +19,7 @@ where the data lives and how each step is computed:
 torch is used for device buffers and the stream only.  There is no CPU fallback: without the CUDA library the
 Context constructor raises.
 """
+import copy
 import time
 
 import numpy as np
@@ -120,6 +121,7 @@ class GpuProver:
         self.stream = torch.cuda.Stream(device=self.device)
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.ctx = Context(device, stream=self.stream.cuda_stream)
+        self._airs = {}
 
     # ---- helpers
     def _to_device(self, a):
@@ -170,7 +172,15 @@ class GpuProver:
 
         trace = stark.generate_trace(witness)
         n = len(trace)
-        air = Air(cfg, n, stark.get_public_inputs(), options)
+        # the AIR bookkeeping and its two compiled evaluator programs depend on (AirConfig, trace length, options) only:
+        # built once per prover, then shared by every proof (public inputs and verifier randomness are bound per proof)
+        key = (cfg, n, options)
+        if key not in self._airs:
+            self._airs[key] = Air(cfg, n, None, options)
+            self._airs[key].composition_program()
+            self._airs[key].deep_program()
+        air = copy.copy(self._airs[key])
+        air.public_inputs = stark.get_public_inputs()
         channel = ProverChannel(air, stark.gen_public_coin(air), ctx)
         fq = FP if cfg.FQ_IS_FP else FQ3
         log_n = air.log_n
@@ -238,8 +248,7 @@ class GpuProver:
         log_ce = log_n + ce_blowup.bit_length() - 1
         M = n * ce_blowup
         composition_coeffs = [channel.public_coin.draw() for _ in range(air.num_composition_constraint_coeffs())]
-        expr = air.substitute_composition_coeffs(composition_coeffs)
-        prog = E.compile_program(expr, nbase, challenges=challenges, hints=hints, lde_step=ce_blowup, log_ce=log_ce)
+        prog = air.composition_program().bind(challenges=challenges, hints=hints, ccoefs=composition_coeffs)
         comp_evals = self._empty(M * fq)
         ctx.eval_constraints(prog, comp_evals, log_ce, base_cols=base_lde, nbase=nbase, base_stride=N,
                              ext_cols=ext_lde, next_=next_, ext_stride=N, fq_field=fq, offset=GEN_MONT, trace_bitrev=True)
@@ -289,11 +298,11 @@ class GpuProver:
 
         # ---- DEEP composition polynomial, evaluated straight over the LDE domain (composer.rs:89-188 in evaluation form)
         ex_alphas, co_alphas, (d_alpha, d_beta) = stark.gen_deep_coeffs(channel.public_coin, air)
-        dexpr = deep.deep_expression(trace_arguments, nbase, next_, ce_blowup, z_points, z_m,
-                                     [_lift(v) for v in execution_trace_oods], [_lift(v) for v in composition_trace_oods],
-                                     [_lift(v) for v in ex_alphas], [_lift(v) for v in co_alphas], _lift(d_alpha), _lift(d_beta))
+        dprog_sym, dkeys = air.deep_program()
+        dprog = dprog_sym.bind(hints=deep.deep_hint_values(
+            dkeys, z_points, z_m, [_lift(v) for v in execution_trace_oods], [_lift(v) for v in composition_trace_oods],
+            [_lift(v) for v in ex_alphas], [_lift(v) for v in co_alphas], _lift(d_alpha), _lift(d_beta)))
         ncols_all = nbase + next_ + ce_blowup
-        dprog = E.compile_program(dexpr, nbase, log_ce=log_N)
         sz = N * 8
         cols = [base_lde.data_ptr() + c * sz for c in range(nbase)]
         cols += [ext_lde.data_ptr() + c * sz * fq for c in range(next_)]

@@ -247,3 +247,21 @@ def test_pow_grind_smallest_nonce(ctx, orc):
     for tag, bits in ((b"a", 0), (b"b", 8), (b"c", 16), (b"d", 20)):
         seed = hashlib.sha256(tag).digest()
         assert ctx.pow_grind(seed, bits) == orc.pow_grind(seed, bits)
+
+
+@pytest.mark.parametrize("log_ff", [1, 2, 3, 4])
+def test_fri_fold_structured_codewords(ctx, orc, log_ff):
+    """few-valued codewords (constants, 2^63 / 2^62 pairs whose sums hit 2^64 exactly, 0/1 flags): the in-register
+    inverse DFT of the fold starts with both-lazy additions"""
+    log_n = 12
+    n = 1 << log_n
+    rng = np.random.default_rng(log_ff)
+    pool = np.array([0, ms.ONE, 2**63, 2**62, ms.P - 1, ms.P - 2**63, 2**32, 2**32 - 2], dtype=np.uint64)
+    alpha = orc.rand_matrix(1, 1, 3, seed=9)[0]
+    for lanes in (1, 3):
+        for pick in (pool[rng.integers(0, 4, size=n * lanes)], np.full(n * lanes, 2**63, dtype=np.uint64),
+                     pool[(np.arange(n * lanes) // 3) % len(pool)]):
+            ev = np.ascontiguousarray(pick, dtype=np.uint64)
+            out = np.empty((n >> log_ff) * lanes, dtype=np.uint64)
+            ctx.fri_fold(ev, out, lanes, log_n, log_ff, alpha)
+            assert np.array_equal(out, orc.fri_apply_drp(ev, lanes, log_n, log_ff, alpha))
