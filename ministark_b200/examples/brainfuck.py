@@ -205,6 +205,27 @@ class BrainfuckTrace(Trace):
         base[MEM_VAL_INV] = inv_lut[ints[MEM_VAL]]
         super().__init__(base, self._extension)
 
+    def helper_columns(self):
+        """0/1 row conditions (and the values they gate) that look at neighbouring rows or at opcodes — functions of the
+        base trace only, computed once with vectorised numpy; Montgomery words (v * (2^32 - 1) needs no reduction)"""
+        if getattr(self, "_aux", None) is None:
+            col = lambda c: self.int_cols[c]
+            n = len(self.rows)
+            ci, mv = col(CURR_INSTR), col(MEM_VAL)
+            nxt_mv = np.concatenate([mv[1:], mv[:1]])
+            iip, ici = col(I_IP), col(I_CURR_INSTR)
+            prev_ip = np.concatenate([[-1], iip[:-1]])
+            aux = np.stack([
+                ci != 0,                                               # 0 processor row is not padding
+                ci == READ, (ci == READ) * nxt_mv,                     # 1, 2
+                ci == WRITE, (ci == WRITE) * nxt_mv,                   # 3, 4
+                col(M_DUMMY) == 0,                                     # 5 memory row is real
+                (ici != 0) & (np.arange(n) > 0) & (iip == prev_ip),    # 6 instruction permutation advances
+                iip != prev_ip,                                        # 7 program evaluation advances
+            ]).astype(np.uint64)
+            self._aux = aux * np.uint64(0xFFFFFFFF)
+        return self._aux
+
     def build_extension_columns_device(self, challenges, ctx, base_dev):
         return _device_extension(self, [tuple(c) for c in challenges], ctx, base_dev)
 
@@ -272,22 +293,9 @@ def _device_extension(trace, ch, ctx, base_dev):
     rows on the host (vectorised numpy, a few bytes per row)."""
     import torch
     from .. import FP, FQ3, ONE
-    col = lambda c: trace.int_cols[c]                                        # small integers (MemValInv is not needed)
     n = len(trace.rows)
     log_n = n.bit_length() - 1
-    ci, mv = col(CURR_INSTR), col(MEM_VAL)
-    nxt_mv = np.concatenate([mv[1:], mv[:1]])
-    iip, ici = col(I_IP), col(I_CURR_INSTR)
-    prev_ip = np.concatenate([[-1], iip[:-1]])
-    aux = np.stack([
-        ci != 0,                                               # 0 processor row is not padding
-        ci == READ, (ci == READ) * nxt_mv,                     # 1, 2
-        ci == WRITE, (ci == WRITE) * nxt_mv,                   # 3, 4
-        col(M_DUMMY) == 0,                                     # 5 memory row is real
-        (ici != 0) & (np.arange(n) > 0) & (iip == prev_ip),    # 6 instruction permutation advances
-        iip != prev_ip,                                        # 7 program evaluation advances
-    ]).astype(np.uint64)
-    aux = aux * np.uint64(0xFFFFFFFF)          # Montgomery words: v * (2^64 mod p) needs no reduction for v < 2^32
+    aux = trace.helper_columns()
     d_aux = torch.from_numpy(aux.view(np.int64)).to(base_dev.device)
     NB = 17
     AUX = lambda k: E.Trace(NB + k, 0)
