@@ -235,8 +235,11 @@ def workload_config(args):
             "l2_policy": "inputs (>= 4 GiB per phase) far exceed the 126 MB L2; no explicit flush",
             "parallelism": ("single GPU" if args.gpus == 1 else
                             f"{args.gpus} ranks: one {args.ncols * args.gpus}-column trace, {args.ncols}-column block per rank "
-                            "(iNTT/LDE local), all-to-all into row slabs for the leaf hash, all-gather of subtree roots "
-                            "and of the partial composition sums")}
+                            "(iNTT/LDE local), " +
+                            ("LDE then NCCL all-to-all into row slabs" if args.no_fused_exchange else
+                             "LDE whose last pass stores each coset block into the owner's row slab over NVLink (CUDA IPC peer "
+                             "memory; no all-to-all)") +
+                            " for the leaf hash, all-gather of subtree roots and of the partial composition sums")}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -275,7 +278,9 @@ def run_gpu(args):
         # the composition is a sum over column-local constraint groups: partial sums are all-gathered and added
         from ministark_b200 import parallel
         sharded = parallel.ShardedCommit(parallel.CudaEngine(ctx, dev), dist, log_n, log_b, ncols * world,
-                                         polys=polys, lde=lde)
+                                         polys=polys, lde=lde, fused=False if args.no_fused_exchange else None)
+        if sharded.fused:
+            pipe.lde_fn = sharded.lde_columns
         partials = torch.empty((world, n), dtype=torch.int64, device=dev)
 
     def commit():
@@ -293,7 +298,10 @@ def run_gpu(args):
         ev[0].record()
         ctx.ntt_batch_to(trace, polys, ms.FP, log_n, ncols, inverse=True)
         ev[1].record()
-        ctx.lde_batch(polys, lde, ms.FP, log_n, log_b, ncols, offset=ms.GENERATOR, bitrev=True)
+        if sharded is not None and sharded.fused:
+            sharded.lde_columns(0, ncols)          # last pass stores the blocks into the owners' row slabs (peer memory)
+        else:
+            ctx.lde_batch(polys, lde, ms.FP, log_n, log_b, ncols, offset=ms.GENERATOR, bitrev=True)
         ev[2].record()
         root = commit()                                                                # D2H of the 32-byte root
         ev[3].record()
@@ -428,6 +436,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="resident steps only (for ncu captures)")
     ap.add_argument("--no-prover", action="store_true", help="skip the examples/fib full-prove sample")
+    ap.add_argument("--no-fused-exchange", action="store_true", help="N > 1: LDE then NCCL all-to-all instead of the fused scatter")
     args = ap.parse_args()
     args.cpu_log_n = min(args.cpu_log_n, args.log_n)
     if args.impl == "reference":

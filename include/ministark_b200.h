@@ -161,6 +161,22 @@ int ms_gather_rows(ms_ctx *ctx, int field, const void *cols, size_t col_stride_e
 int ms_gather_rows_rowmajor(ms_ctx *ctx, const void *rows, unsigned row_words, size_t nrows, const uint64_t *row_ids,
                             unsigned nq, void *out);
 
+/* ---- multi-GPU: LDE fused with the exchange into row slabs ----
+ * one process per GPU; the bit-reversed LDE is 2^log_blowup coset blocks of n rows and, with G | 2^log_blowup GPUs,
+ * the row slab a GPU hashes is a run of whole blocks.  The last NTT pass stores block q of every local column at
+ * block_ptrs[q] + column * block_col_stride_elems (element units) — block_ptrs[q] may point into a PEER GPU's slab
+ * (mapped with ms_ipc_open), so the all-to-all disappears into the LDE's own stores over NVLink.  dup_ptrs (or NULL;
+ * entries may be NULL): a second copy of block q, e.g. the local ce-domain prefix.  work: ncols x work_stride_elems
+ * resident scratch for the earlier passes.  The caller synchronises the ranks (barrier) before reading a slab. */
+int ms_lde_batch_scatter(ms_ctx *ctx, int field, const void *coeffs, size_t in_stride_elems, unsigned ncols, unsigned log_n,
+                         unsigned log_blowup, uint64_t offset_mont, void *work, size_t work_stride_elems,
+                         void *const *block_ptrs, size_t block_col_stride_elems, void *const *dup_ptrs,
+                         size_t dup_col_stride_elems);
+/* CUDA IPC: export a buffer obtained from ms_alloc_device (handle: 64 bytes), map / unmap a peer's buffer */
+int ms_ipc_export(ms_ctx *ctx, const void *dev_ptr, uint8_t *handle64);
+int ms_ipc_open(ms_ctx *ctx, const uint8_t *handle64, void **peer_ptr);
+int ms_ipc_close(ms_ctx *ctx, void *peer_ptr);
+
 /* ---- trace generation: running products / running evaluations as a parallel scan ----
  * the sequential column builders of examples/brainfuck/trace.rs:108-279 and examples/fib/main.rs:175-222:
  *     x_0 = init,  x_(i+1) = x_i * a_i + b_i,      out[i] = x_i (inclusive == 0) or x_(i+1) (inclusive != 0)

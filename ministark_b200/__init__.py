@@ -127,6 +127,40 @@ class Context:
         self._ck(self.lib.ms_lde_batch(self.h, field, _ptr(coeffs), in_stride, _ptr(evals), out_stride, ncols,
                                        log_n, log_blowup, offset, int(bitrev)))
 
+    def lde_batch_scatter(self, coeffs, work, field, log_n, log_blowup, ncols, block_ptrs, block_col_stride, dup_ptrs=None,
+                          dup_col_stride=0, in_stride=None, work_stride=None, offset=GENERATOR):
+        """bit-reversed coset LDE whose last pass stores coset block q of the local columns at block_ptrs[q] (raw
+        device addresses, possibly peer memory) and optionally a second copy at dup_ptrs[q] (multi-GPU fused exchange)"""
+        nb = 1 << log_blowup
+        n = 1 << log_n
+        bp = (C.c_void_p * nb)(*[int(p) for p in block_ptrs])
+        dp = (C.c_void_p * nb)(*[int(p) if p else None for p in dup_ptrs]) if dup_ptrs is not None else None
+        self._ck(self.lib.ms_lde_batch_scatter(self.h, field, _ptr(coeffs), n if in_stride is None else in_stride, ncols, log_n,
+                                               log_blowup, offset, _ptr(work), (n << log_blowup) if work_stride is None else work_stride,
+                                               bp, block_col_stride, dp, dup_col_stride))
+
+    # ---- raw device buffers and CUDA IPC (peer slabs of the multi-GPU commit)
+    def alloc_device(self, nbytes):
+        out = C.c_void_p()
+        self._ck(self.lib.ms_alloc_device(self.h, nbytes, C.byref(out)))
+        return int(out.value)
+
+    def free(self, ptr):
+        self._ck(self.lib.ms_free(self.h, ptr))
+
+    def ipc_export(self, ptr):
+        h = (C.c_uint8 * 64)()
+        self._ck(self.lib.ms_ipc_export(self.h, ptr, h))
+        return bytes(h)
+
+    def ipc_open(self, handle):
+        out = C.c_void_p()
+        self._ck(self.lib.ms_ipc_open(self.h, (C.c_uint8 * 64).from_buffer_copy(bytes(handle)), C.byref(out)))
+        return int(out.value)
+
+    def ipc_close(self, ptr):
+        self._ck(self.lib.ms_ipc_close(self.h, ptr))
+
     def bit_reverse(self, data, field, log_n, ncols=1, col_stride=None):
         col_stride = (1 << log_n) if col_stride is None else col_stride
         self._ck(self.lib.ms_bit_reverse(self.h, field, _ptr(data), col_stride, ncols, log_n))

@@ -50,6 +50,10 @@ _SIGS = {
     "ms_gather_rows": (ci, [vp, ci, vp, sz, ui, sz, vp, ui, vp]),
     "ms_gather_rows_rowmajor": (ci, [vp, vp, ui, sz, vp, ui, vp]),
     "ms_debug_lazy_ops": (ci, [vp, vp, vp, sz, vp]),
+    "ms_lde_batch_scatter": (ci, [vp, ci, vp, sz, ui, ui, ui, u64, vp, sz, vp, sz, vp, sz]),
+    "ms_ipc_export": (ci, [vp, vp, vp]),
+    "ms_ipc_open": (ci, [vp, vp, C.POINTER(vp)]),
+    "ms_ipc_close": (ci, [vp, vp]),
     "ms_scan_affine": (ci, [vp, ci, vp, ci, vp, vp, ci, sz, vp, ci, vp]),
     "ms_fri_fold": (ci, [vp, ci, vp, ui, ui, u64, vp, vp]),
     "ms_eval_constraints": (ci, [vp, vp, ui, vp, ui, vp, sz, ui, vp, sz, ui, ci, ui, u64, ci, ci, vp]),

@@ -210,6 +210,7 @@ uint64_t ms_launch_count(ms_ctx *c) { return c ? c->launches : 0; }
 
 int ms_alloc_device(ms_ctx *c, size_t bytes, void **out) {
     if (!c || !out) return MS_ERR_INVALID;
+    cudaSetDevice(c->device);
     cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
     if (e != cudaSuccess) {
         cudaGetLastError();

@@ -270,7 +270,7 @@ __global__ void copy_strided_kernel(const u64 *src, size_t src_stride, u64 *dst,
     if (i < words) dst[blockIdx.y * dst_stride + i] = src[blockIdx.y * src_stride + i];
 }
 
-int ntt_run(ms_ctx *c, NttPlanDev &P, const u64 *in, size_t in_cs, u64 *out, size_t out_cs, unsigned ncols) {
+int ntt_run(ms_ctx *c, NttPlanDev &P, const u64 *in, size_t in_cs, u64 *out, size_t out_cs, unsigned ncols, const LdeScatter *sc) {
     if (ncols == 0) return MS_OK;
     const u64 N = P.N;
     const size_t col_words = (size_t)N * P.estride;
@@ -323,6 +323,14 @@ int ntt_run(ms_ctx *c, NttPlanDev &P, const u64 *in, size_t in_cs, u64 *out, siz
                 p.out_col_stride = out_cs;
                 p.in_cos_stride = (k == 0) ? 0 : col_words;
                 p.out_cos_stride = col_words;
+                if (sc && k == m - 1) {
+                    // fused exchange: the last pass stores every coset block where its rows are needed
+                    if (c0 != 0) return fail(c, MS_ERR_INVALID, "internal: scatter LDE must run in one column batch");
+                    p.out_cos_ptr = sc->block_ptr;
+                    p.out_col_stride = sc->block_col_stride_words;
+                    p.out_dup_ptr = sc->dup_ptr;
+                    p.dup_col_stride = sc->dup_col_stride_words;
+                }
             } else if (m == 1) {
                 pin = src;
                 pout = dst;
@@ -516,6 +524,72 @@ int ms_lde_batch(ms_ctx *c, int field, const void *coeffs, size_t in_stride_elem
     }
     if ((rc = in.finish())) return rc;
     return out.finish();
+}
+
+// ---- fused LDE + exchange (multi-GPU commit, SURVEY.md §8e "fusion opportunity") ---------------------------------
+// The bit-reversed LDE is 2^log_blowup coset blocks of n rows; with G GPUs (G | 2^log_blowup) the row slab of GPU j is
+// a run of whole blocks.  Instead of LDE -> all-to-all, the last NTT pass stores block q of every local column straight
+// into the slab of the GPU that hashes those rows: block_ptrs[q] = address (possibly peer memory mapped with
+// ms_ipc_open) of block q of LOCAL column 0 inside that slab, consecutive local columns block_col_stride_elems apart.
+// dup_ptrs (optional, entries may be NULL): a second copy of block q — e.g. the local copy of the ce-domain prefix the
+// constraint evaluation of this rank's columns reads.  work: ncols x work_stride_elems scratch for the earlier passes.
+int ms_lde_batch_scatter(ms_ctx *c, int field, const void *coeffs, size_t in_stride_elems, unsigned ncols, unsigned log_n,
+                         unsigned log_blowup, uint64_t offset_mont, void *work, size_t work_stride_elems, void *const *block_ptrs,
+                         size_t block_col_stride_elems, void *const *dup_ptrs, size_t dup_col_stride_elems) {
+    if (!c || !coeffs || !work || !block_ptrs) return MS_ERR_INVALID;
+    if (int rc = check_field(c, field)) return rc;
+    if (log_n < 4 || log_n + log_blowup > 32 || log_blowup > 6 || ncols == 0) return fail(c, MS_ERR_INVALID, "ms_lde_batch_scatter: bad size");
+    if (offset_mont >= gl::P || offset_mont == 0) return fail(c, MS_ERR_INVALID, "offset must be a non-zero canonical word");
+    const size_t n = (size_t)1 << log_n, N = n << log_blowup;
+    const unsigned nb = 1u << log_blowup;
+    if (ncols > 1 && (in_stride_elems < n || work_stride_elems < N || block_col_stride_elems < n))
+        return fail(c, MS_ERR_INVALID, "ms_lde_batch_scatter: stride too small");
+    if (!is_device_ptr(coeffs) || !is_device_ptr(work)) return fail(c, MS_ERR_INVALID, "ms_lde_batch_scatter: resident buffers only");
+    for (unsigned q = 0; q < nb; q++)
+        if (!block_ptrs[q]) return fail(c, MS_ERR_INVALID, "ms_lde_batch_scatter: block pointer %u is null", q);
+    cudaSetDevice(c->device);
+    NttJob job{field, log_n, false, true, log_blowup, offset_mont};
+    std::shared_ptr<NttPlanDev> P;
+    int rc;
+    if ((rc = ntt_get_plan(c, job, &P))) return rc;
+    void *tab;
+    if ((rc = scratch_get(c, 1, (size_t)nb * 16, &tab))) return rc;
+    std::vector<void *> host(2 * nb, nullptr);
+    for (unsigned q = 0; q < nb; q++) {
+        host[q] = block_ptrs[q];
+        host[nb + q] = dup_ptrs ? dup_ptrs[q] : nullptr;
+    }
+    MS_CUDA(c, cudaMemcpyAsync(tab, host.data(), (size_t)nb * 16, cudaMemcpyHostToDevice, c->stream));
+    MS_CUDA(c, cudaStreamSynchronize(c->stream));      // host is a stack temporary
+    LdeScatter sc{(u64 *const *)tab, block_col_stride_elems * field, dup_ptrs ? (u64 *const *)tab + nb : nullptr,
+                  dup_col_stride_elems * field};
+    return ntt_run(c, *P, (const u64 *)coeffs, in_stride_elems * field, (u64 *)work, work_stride_elems * field, ncols, &sc);
+}
+
+// CUDA IPC plumbing for the peer slabs (one process per GPU): export a cudaMalloc'ed buffer of this process, map a
+// buffer exported by a peer process.  handle: 64 bytes (cudaIpcMemHandle_t).
+int ms_ipc_export(ms_ctx *c, const void *dev_ptr, uint8_t *handle64) {
+    if (!c || !dev_ptr || !handle64) return MS_ERR_INVALID;
+    cudaSetDevice(c->device);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    MS_CUDA(c, cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+    memcpy(handle64, &h, 64);
+    return MS_OK;
+}
+int ms_ipc_open(ms_ctx *c, const uint8_t *handle64, void **peer_ptr) {
+    if (!c || !handle64 || !peer_ptr) return MS_ERR_INVALID;
+    cudaSetDevice(c->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    MS_CUDA(c, cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return MS_OK;
+}
+int ms_ipc_close(ms_ctx *c, void *peer_ptr) {
+    if (!c || !peer_ptr) return MS_ERR_INVALID;
+    cudaSetDevice(c->device);
+    MS_CUDA(c, cudaIpcCloseMemHandle(peer_ptr));
+    return MS_OK;
 }
 
 }  // extern "C"

@@ -84,7 +84,16 @@ int ntt_get_plan(ms_ctx *c, const NttJob &job, std::shared_ptr<NttPlanDev> *out)
 // two-level table of g_n^e (forward root of unity of order 2^log_n): e = 4096*e1 + e0
 int ntt_plan_tables(ms_ctx *c, unsigned log_n, const u64 **tw_lo, const u64 **tw_hi, u32 *hi_len);
 // run: natural mode: in == out allowed (uses scratch 0).  LDE mode: in -> out.
+// LDE scatter (ms_lde_batch_scatter): the LAST pass writes coset block q of column 0 at block_ptr[q] (device array of
+// 2^log_blowup pointers, entries may be peer-device memory) with column stride block_col_stride, and a second copy at
+// dup_ptr[q] (where non-null) with column stride dup_col_stride; earlier passes work in `out` as usual.
+struct LdeScatter {
+    u64 *const *block_ptr;
+    size_t block_col_stride_words;
+    u64 *const *dup_ptr;
+    size_t dup_col_stride_words;
+};
 int ntt_run(ms_ctx *c, NttPlanDev &plan, const u64 *in, size_t in_col_stride_words, u64 *out,
-            size_t out_col_stride_words, unsigned ncols);
+            size_t out_col_stride_words, unsigned ncols, const LdeScatter *scatter = nullptr);
 
 }  // namespace ms

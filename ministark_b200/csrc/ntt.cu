@@ -45,6 +45,7 @@ struct TileCtx {
     const u64 *pre_tab;
     const u64 *sm2;   // last-step multiplier tile prefetched into shared memory (or nullptr)
     u64 pre_step;
+    u64 *dst2;        // second destination of this CTA's outputs (LDE scatter: local copy of a block) or nullptr
 };
 
 __device__ __forceinline__ void cp_async8(u64 *smem_dst, const u64 *gsrc) {
@@ -179,8 +180,13 @@ __device__ __forceinline__ void do_step(u64 *sm, const PassParams &p, const Tabl
             // straight to global: natural digit -> output row i_R; bit-reversed digit -> row = position
             const idx_t ors = (idx_t)p.out_rs * (idx_t)es;
             if (p.bitrev_digit) {
-                u64 *dp = dst + (tc.out_base + (u64)c * p.out_cs + (u64)rpos0 * p.out_rs) * es;
+                const u64 off = (tc.out_base + (u64)c * p.out_cs + (u64)rpos0 * p.out_rs) * es;
+                u64 *dp = dst + off;
                 static_for<0, RAD>([&](auto Q) { dp[(idx_t)Q * ors] = x[Q]; });
+                if (tc.dst2) {
+                    u64 *dp2 = tc.dst2 + off;
+                    static_for<0, RAD>([&](auto Q) { dp2[(idx_t)Q * ors] = x[Q]; });
+                }
             } else {
                 constexpr int SH = B1 + B2;
                 u64 *dp = dst + (tc.out_base + (u64)c * p.out_cs + (u64)iR0 * p.out_rs) * es;
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, co
     const u32 cos = b & (p.ncos - 1);
     const u32 col = b >> p.log_ncos;
     const u64 *src = in + (u64)col * p.in_col_stride + (u64)cos * p.in_cos_stride + lane;
-    u64 *dst = out + (u64)col * p.out_col_stride + (u64)cos * p.out_cos_stride + lane;
+    u64 *dst = (p.out_cos_ptr ? p.out_cos_ptr[cos] : out + (u64)cos * p.out_cos_stride) + (u64)col * p.out_col_stride + lane;
 
     // ---- tile decode
     TileCtx tc;
@@ -242,6 +248,11 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, co
     tc.sc_hi = tb.sc_hi ? tb.sc_hi + (u64)cos * p.hi_len : nullptr;
     tc.pre_step = (p.has_pre && tb.pre_step) ? tb.pre_step[cos] : 0;
     tc.pre_tab = p.pre_tab ? p.pre_tab + (u64)cos * p.pre_cos_stride : nullptr;
+    tc.dst2 = nullptr;
+    if (p.out_dup_ptr) {
+        u64 *b2 = p.out_dup_ptr[cos];
+        if (b2) tc.dst2 = b2 + (u64)col * p.dup_col_stride + lane;
+    }
 
     // ---- prefetch the last step's multiplier tile (inter-pass twiddles, or the inverse post-scale) into
     //      the second shared buffer with cp.async: it lands while the sub-NTT runs
@@ -335,11 +346,15 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, co
     {
         using idx_t = typename std::conditional<(LW >= 0), u32, u64>::type;
         u64 *dp = dst + tc.out_base * es;
+        u64 *dp2 = tc.dst2 ? tc.dst2 + tc.out_base * es : nullptr;
 #pragma unroll 4
         for (int k = 0; k < kElemsPerThread; k++) {
             const u32 i = k * nthreads + tid;
             const u32 rho = i & (R - 1), c = i >> LOGR;
-            dp[((idx_t)rho * (idx_t)p.out_rs + (idx_t)c * (idx_t)p.out_cs) * (idx_t)es] = sm[padi((pos_of(rho) << lw) + c)];
+            const idx_t o = ((idx_t)rho * (idx_t)p.out_rs + (idx_t)c * (idx_t)p.out_cs) * (idx_t)es;
+            const u64 v = sm[padi((pos_of(rho) << lw) + c)];
+            dp[o] = v;
+            if (dp2) dp2[o] = v;
         }
     }
 }

@@ -55,6 +55,12 @@ struct PassParams {
     const u64 *pre_tab;                  // [cos * pre_cos_stride + j] = q_cos^j
     u64 pre_cos_stride;
     const u64 *post_tab;                 // [i] = c * q^i
+    // LDE scatter (fused exchange, multi-GPU): when set, coset block `cos` of column 0 is written at out_cos_ptr[cos]
+    // (a pointer that may live on a PEER device, reached over NVLink) instead of out + cos * out_cos_stride, and —
+    // where out_dup_ptr[cos] is non-null — a second copy at out_dup_ptr[cos] with its own column stride.
+    u64 *const *out_cos_ptr = nullptr;
+    u64 *const *out_dup_ptr = nullptr;
+    u64 dup_col_stride = 0;              // words
 };
 
 struct Tables {

@@ -11,6 +11,11 @@ path shards like this:
            needs every column of its row (src/hash.rs:92-99), so some row-wise exchange is
            unavoidable; volume (G-1)/G of the LDE per GPU over NVLink
   phase B  (row sharded)  leaf hashes + Merkle subtree of the local row slab   (src/merkle.rs:412-508)
+  fused    (CUDA engine, G | blow-up) the exchange disappears into the LDE: the bit-reversed LDE is 2^log_blowup coset
+           blocks of n rows and a row slab is a run of whole blocks, so the last NTT pass stores every block straight
+           into the slab of the GPU that hashes it — peer memory mapped with CUDA IPC, written over NVLink/NVSwitch
+           (ms_lde_batch_scatter) — plus a local copy of the ce-domain prefix; two barriers per step replace the
+           all-to-all (writers done before the slab is hashed; hashing done before the slab is overwritten)
   commit   all-gather of the G subtree roots (32 B each); every rank finishes the top log2(G)
            levels -> the same root as the single-device tree               (src/merkle.rs:485-508)
            all-gather of the partial composition columns, summed locally.
@@ -56,7 +61,7 @@ class ShardedCommit:
                                                            for nrows == 1 the single leaf digest
     """
 
-    def __init__(self, engine, dist, log_n, log_blowup, ncols_total, polys=None, lde=None):
+    def __init__(self, engine, dist, log_n, log_blowup, ncols_total, polys=None, lde=None, fused=None, dup_blocks=1):
         self.e, self.dist = engine, dist
         self.world = dist.get_world_size() if dist is not None else 1
         self.rank = dist.get_rank() if dist is not None else 0
@@ -72,18 +77,56 @@ class ShardedCommit:
         n = 1 << log_n
         self.polys = polys if polys is not None else engine.empty((self.nloc, n))
         self.lde = lde if lde is not None else engine.empty((self.nloc, self.N))
-        self.slab = engine.empty((ncols_total, self.rows_per)) if self.world > 1 else None
+        self.fused, self.dup_blocks = False, dup_blocks
+        nblocks = 1 << log_blowup
+        can_fuse = (self.world > 1 and getattr(engine, "peer_scatter", False) and nblocks % self.world == 0 and log_n >= 4)
+        if fused and not can_fuse:
+            raise ValueError("fused exchange needs the CUDA engine and a world size dividing the blow-up factor")
+        if can_fuse and fused is not False:
+            # every rank exports its slab; block q of the bit-reversed LDE lives in the slab of rank q // (blocks per rank)
+            self.slab, self._slab_ptr = engine.alloc_exportable((ncols_total, self.rows_per))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, engine.ipc_export(self._slab_ptr))
+            self._peer = [self._slab_ptr if r == self.rank else engine.ipc_open(handles[r]) for r in range(self.world)]
+            self._need_barrier = False
+            self.fused = True
+        else:
+            self.slab = engine.empty((ncols_total, self.rows_per)) if self.world > 1 else None
 
     def transform(self, trace):
         """phase A on the local columns: trace (nloc, n) -> self.polys, self.lde"""
         self.e.intt(trace, self.polys, self.log_n, self.nloc)
-        self.e.lde(self.polys, self.lde, self.log_n, self.log_b, self.nloc)
+        self.lde_columns(0, self.nloc)
         return self.lde
+
+    def lde_columns(self, c0, k):
+        """coset LDE of local columns [c0, c0 + k) of self.polys.  Fused mode: the blocks go straight into the owners'
+        slabs (and the first `dup_blocks` blocks also into self.lde, where the local constraint evaluation reads the
+        ce-domain prefix); self.lde doubles as the work buffer of the earlier passes."""
+        if not self.fused:
+            self.e.lde(self.polys[c0:c0 + k], self.lde[c0:c0 + k], self.log_n, self.log_b, k)
+            return
+        if self._need_barrier:           # nobody may still be hashing the slab this LDE is about to overwrite
+            self.e.sync()
+            self.dist.barrier()
+            self._need_barrier = False
+        n, nblocks = 1 << self.log_n, 1 << self.log_b
+        per_rank = nblocks // self.world
+        col = self.lo + c0
+        blocks = [self._peer[q // per_rank] + (col * self.rows_per + (q % per_rank) * n) * 8 for q in range(nblocks)]
+        lde_ptr = self.e.ptr(self.lde) + c0 * self.N * 8
+        dups = [lde_ptr + q * n * 8 if q < self.dup_blocks else 0 for q in range(nblocks)]
+        self.e.lde_scatter(self.polys[c0:c0 + k], lde_ptr, self.log_n, self.log_b, k, blocks, self.rows_per, dups, self.N)
 
     def exchange(self):
         """all-to-all into row slabs; returns the (ncols_total, rows_per) slab of this rank"""
         if self.world == 1:
             return self.lde
+        if self.fused:
+            self.e.sync()                # this rank's stores into the peers' slabs are complete ...
+            self.dist.barrier()          # ... and so are everybody else's into ours
+            self._need_barrier = True
+            return self.slab
         per = self.nloc
         sends, recvs = [], []
         for c in range(per):
@@ -132,6 +175,39 @@ class CudaEngine:
 
     def view(self, buf, col, lo, hi):
         return buf[col, lo:hi]
+
+    # ---- peer slabs (fused exchange)
+    peer_scatter = True
+
+    def ptr(self, buf):
+        return buf.data_ptr()
+
+    def sync(self):
+        self.ctx.sync()
+
+    def alloc_exportable(self, shape):
+        """a cudaMalloc'ed buffer (exportable with CUDA IPC, unlike a sub-allocation of torch's caching allocator)
+        wrapped as a torch tensor"""
+        nwords = int(np.prod(shape))
+        ptr = self.ctx.alloc_device(nwords * 8)
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (nwords,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+        self._raw = getattr(self, "_raw", []) + [_Raw]
+        t = self.torch.as_tensor(_Raw(), device=self.device).view(*shape)
+        return t, ptr
+
+    def ipc_export(self, ptr):
+        return self.ctx.ipc_export(ptr)
+
+    def ipc_open(self, handle):
+        return self.ctx.ipc_open(handle)
+
+    def lde_scatter(self, coeffs, work_ptr, log_n, log_b, ncols, block_ptrs, block_stride, dup_ptrs, dup_stride):
+        from . import GENERATOR
+        self.ctx.lde_batch_scatter(coeffs, work_ptr, 1, log_n, log_b, ncols, block_ptrs, block_stride, dup_ptrs, dup_stride,
+                                   offset=GENERATOR)
 
     def intt(self, src, dst, log_n, ncols):
         self.ctx.ntt_batch_to(src, dst, 1, log_n, ncols, inverse=True)

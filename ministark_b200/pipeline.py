@@ -18,12 +18,13 @@ from . import FP, GENERATOR
 
 
 class TraceCommitPipeline:
-    def __init__(self, ctx, device, log_n, log_blowup, ncols, evaluator=None, chunk_cols=4, stream=None):
+    def __init__(self, ctx, device, log_n, log_blowup, ncols, evaluator=None, chunk_cols=4, stream=None, lde_fn=None):
         self.ctx, self.device = ctx, device
         self.log_n, self.log_b, self.ncols = log_n, log_blowup, ncols
         self.n, self.N = 1 << log_n, 1 << (log_n + log_blowup)
         self.chunk = max(1, min(chunk_cols, ncols))
         self.evaluator = evaluator
+        self.lde_fn = lde_fn          # multi-GPU: ShardedCommit.lde_columns (LDE fused with the exchange into row slabs)
         self.compute = stream if stream is not None else torch.cuda.current_stream(device)
         self.copy = torch.cuda.Stream(device=device)
         i64 = torch.int64
@@ -40,7 +41,10 @@ class TraceCommitPipeline:
         c1 = self.ncols if c1 is None else c1
         k = c1 - c0
         self.ctx.ntt_batch_to(self.trace[c0], self.polys[c0], FP, self.log_n, k, inverse=True)
-        self.ctx.lde_batch(self.polys[c0], self.lde[c0], FP, self.log_n, self.log_b, k, offset=GENERATOR, bitrev=True)
+        if self.lde_fn is not None:
+            self.lde_fn(c0, k)
+        else:
+            self.ctx.lde_batch(self.polys[c0], self.lde[c0], FP, self.log_n, self.log_b, k, offset=GENERATOR, bitrev=True)
 
     def commit(self):
         return self.ctx.merkle_commit(self.lde, FP, self.N, self.ncols, leaves=self.leaves, nodes=self.nodes)

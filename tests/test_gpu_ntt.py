@@ -254,3 +254,31 @@ def test_structured_columns_all_transforms(ctx, orc, log_n):
     got = q.copy()
     ctx.ntt_batch(got, ms.FQ3, log_n, 1, inverse=True)
     assert np.array_equal(got, orc.ntt(q, 3, log_n, inverse=True))
+
+
+@pytest.mark.parametrize("log_n,log_b,ncols,field", [(10, 3, 5, 1), (13, 3, 3, 1), (16, 2, 4, 1), (5, 3, 2, 1), (12, 3, 2, 3), (4, 1, 3, 1)])
+@pytest.mark.parametrize("world", [2, 4])
+def test_lde_scatter_into_row_slabs(ctx, orc, log_n, log_b, ncols, field, world):
+    """ms_lde_batch_scatter (the multi-GPU fused exchange) with the "peer" slabs on the same device: every coset block
+    lands in the slab that owns its rows, at the column offset of this rank, plus a local copy of block 0"""
+    torch = pytest.importorskip("torch")
+    nb = 1 << log_b
+    if nb % world:
+        pytest.skip("world must divide the blow-up")
+    n, N = 1 << log_n, 1 << (log_n + log_b)
+    rows_per, per_rank = N // world, nb // world
+    total_cols, lo = ncols + 3, 2                          # the local columns are global columns [lo, lo + ncols)
+    coeffs = orc.rand_matrix(ncols, n, field, seed=log_n + world)
+    want = orc.lde(coeffs, field, log_n, log_b, orc.generator(), True)
+    d_coeffs = torch.from_numpy(coeffs.view(np.int64)).cuda()
+    work = torch.zeros((ncols, N * field), dtype=torch.int64, device="cuda")
+    slabs = [torch.zeros((total_cols, rows_per * field), dtype=torch.int64, device="cuda") for _ in range(world)]
+    blocks = [slabs[q // per_rank].data_ptr() + (lo * rows_per + (q % per_rank) * n) * field * 8 for q in range(nb)]
+    dups = [work.data_ptr() if q == 0 else 0 for q in range(nb)]
+    ctx.lde_batch_scatter(d_coeffs, work, field, log_n, log_b, ncols, blocks, rows_per, dups, N)
+    ctx.sync()
+    for j in range(world):
+        got = slabs[j].cpu().numpy().view(np.uint64)
+        assert np.array_equal(got[lo:lo + ncols], want[:, j * rows_per * field:(j + 1) * rows_per * field]), j
+        assert not got[:lo].any() and not got[lo + ncols:].any()          # other ranks' columns untouched
+    assert np.array_equal(work.cpu().numpy().view(np.uint64)[:, :n * field], want[:, :n * field])
