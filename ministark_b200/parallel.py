@@ -83,14 +83,31 @@ class ShardedCommit:
         if fused and not can_fuse:
             raise ValueError("fused exchange needs the CUDA engine and a world size dividing the blow-up factor")
         if can_fuse and fused is not False:
-            # every rank exports its slab; block q of the bit-reversed LDE lives in the slab of rank q // (blocks per rank)
-            self.slab, self._slab_ptr = engine.alloc_exportable((ncols_total, self.rows_per))
+            # every rank exports its slab; block q of the bit-reversed LDE lives in the slab of rank q // (blocks per rank).
+            # All ranks must end up in the same mode: a rank whose IPC setup fails makes everybody fall back to NCCL.
+            ok, err = 1, None
+            try:
+                self.slab, self._slab_ptr = engine.alloc_exportable((ncols_total, self.rows_per))
+                handle = engine.ipc_export(self._slab_ptr)
+            except Exception as exc:          # noqa: BLE001 — any failure here only selects the fallback path
+                ok, err, handle = 0, exc, None
             handles = [None] * self.world
-            dist.all_gather_object(handles, engine.ipc_export(self._slab_ptr))
-            self._peer = [self._slab_ptr if r == self.rank else engine.ipc_open(handles[r]) for r in range(self.world)]
-            self._need_barrier = False
-            self.fused = True
-        else:
+            dist.all_gather_object(handles, handle)
+            if ok and all(h is not None for h in handles):
+                try:
+                    self._peer = [self._slab_ptr if r == self.rank else engine.ipc_open(handles[r]) for r in range(self.world)]
+                except Exception as exc:      # noqa: BLE001
+                    ok, err = 0, exc
+            else:
+                ok = 0
+            flags = [None] * self.world
+            dist.all_gather_object(flags, ok)
+            if all(flags):
+                self._need_barrier = False
+                self.fused = True
+            elif fused:
+                raise RuntimeError(f"fused exchange requested but the peer-slab setup failed on some rank: {err}")
+        if not self.fused:
             self.slab = engine.empty((ncols_total, self.rows_per)) if self.world > 1 else None
 
     def transform(self, trace):
