@@ -211,7 +211,9 @@ struct Steps {
     static constexpr int C = N == 3 ? LOGR - A - Bb : 0;
 };
 
-template <int LOGR, int LW, bool INV>
+// SC: LDE scatter (destination per coset block from a pointer table + optional second copy); a separate instantiation
+// so that the ordinary passes keep their single-destination store path
+template <int LOGR, int LW, bool INV, bool SC = false>
 __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, const Tables tb, const u64 *__restrict__ in,
                                                           u64 *__restrict__ out) {
     extern __shared__ u64 sm[];
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, co
     const u32 cos = b & (p.ncos - 1);
     const u32 col = b >> p.log_ncos;
     const u64 *src = in + (u64)col * p.in_col_stride + (u64)cos * p.in_cos_stride + lane;
-    u64 *dst = (p.out_cos_ptr ? p.out_cos_ptr[cos] : out + (u64)cos * p.out_cos_stride) + (u64)col * p.out_col_stride + lane;
+    u64 *dst = (SC ? p.out_cos_ptr[cos] : out + (u64)cos * p.out_cos_stride) + (u64)col * p.out_col_stride + lane;
 
     // ---- tile decode
     TileCtx tc;
@@ -249,9 +251,11 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, co
     tc.pre_step = (p.has_pre && tb.pre_step) ? tb.pre_step[cos] : 0;
     tc.pre_tab = p.pre_tab ? p.pre_tab + (u64)cos * p.pre_cos_stride : nullptr;
     tc.dst2 = nullptr;
-    if (p.out_dup_ptr) {
-        u64 *b2 = p.out_dup_ptr[cos];
-        if (b2) tc.dst2 = b2 + (u64)col * p.dup_col_stride + lane;
+    if constexpr (SC) {
+        if (p.out_dup_ptr) {
+            u64 *b2 = p.out_dup_ptr[cos];
+            if (b2) tc.dst2 = b2 + (u64)col * p.dup_col_stride + lane;
+        }
     }
 
     // ---- prefetch the last step's multiplier tile (inter-pass twiddles, or the inverse post-scale) into
@@ -346,7 +350,7 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, co
     {
         using idx_t = typename std::conditional<(LW >= 0), u32, u64>::type;
         u64 *dp = dst + tc.out_base * es;
-        u64 *dp2 = tc.dst2 ? tc.dst2 + tc.out_base * es : nullptr;
+        u64 *dp2 = (SC && tc.dst2) ? tc.dst2 + tc.out_base * es : nullptr;
 #pragma unroll 4
         for (int k = 0; k < kElemsPerThread; k++) {
             const u32 i = k * nthreads + tid;
@@ -354,7 +358,7 @@ __global__ void __launch_bounds__(256, 3) ntt_pass_kernel(const PassParams p, co
             const idx_t o = ((idx_t)rho * (idx_t)p.out_rs + (idx_t)c * (idx_t)p.out_cs) * (idx_t)es;
             const u64 v = sm[padi((pos_of(rho) << lw) + c)];
             dp[o] = v;
-            if (dp2) dp2[o] = v;
+            if (SC && dp2) dp2[o] = v;
         }
     }
 }
@@ -377,10 +381,18 @@ static void launch_t(const PassParams &p, const Tables &t, bool inverse, const u
     }
     const unsigned ty = ntiles < 32768u ? ntiles : 32768u;   // ntiles is a power of two
     dim3 grid(nbatch, ty, ntiles / ty);
-    if (inverse)
+    if (inverse) {
         ntt_pass_kernel<LOGR, LW, true><<<grid, threads, smem, stream>>>(p, t, in, out);
-    else
+    } else if (p.out_cos_ptr) {
+        static bool attr_sc[64] = {false};
+        if (dev < 0 || dev >= 64 || !attr_sc[dev]) {
+            cudaFuncSetAttribute(ntt_pass_kernel<LOGR, LW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+            if (dev >= 0 && dev < 64) attr_sc[dev] = true;
+        }
+        ntt_pass_kernel<LOGR, LW, false, true><<<grid, threads, smem, stream>>>(p, t, in, out);
+    } else {
         ntt_pass_kernel<LOGR, LW, false><<<grid, threads, smem, stream>>>(p, t, in, out);
+    }
 }
 
 void launch_pass(const PassParams &p, const Tables &t, bool inverse, const u64 *in, u64 *out, unsigned ntiles,
