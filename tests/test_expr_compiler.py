@@ -1,0 +1,188 @@
+"""CPU-only: the constraint-expression compiler (ministark_b200/expr.py) — operand ordering, register allocation with
+leaf rematerialisation under the 48-register limit, constant folding, Div -> Mul/Inv rewriting, symbolic constants and
+Program.bind — checked by EXECUTING the emitted programs with a big-integer interpreter of the evaluator's instruction
+set (csrc/eval.cu) and comparing with a direct recursive evaluation of the expression DAG."""
+import random
+
+import numpy as np
+import pytest
+
+from ministark_b200 import expr as E
+from ministark_b200.air import Air, CompositionCoeff, ProofOptions
+from ministark_b200.examples import brainfuck as bf
+from ministark_b200.examples import fib, perm
+
+P = E.P
+R = 2**64
+RINV = pow(R, -1, P)
+
+
+def run_program(prog, x, cols, col_is_q, row, m):
+    """big-int interpreter of the 4-word instructions; returns the stored Fq element (3-tuple of canonical ints)"""
+    regs = {}
+    out = None
+    for op_w, d, a, b in prog.code.tolist():
+        op, qa, qb = op_w & 0xFF, (op_w >> 8) & 1, (op_w >> 9) & 1
+        if op == E.OP_X:
+            regs[d] = (x, 0, 0)
+        elif op == E.OP_CONST:
+            regs[d] = tuple(int(w) * RINV % P for w in prog.consts[a])
+        elif op == E.OP_TRACE:
+            v = cols[a][(row + b) % m]
+            assert bool(qa) == bool(col_is_q[a])
+            regs[d] = tuple(v) if qa else (v, 0, 0)
+        elif op == E.OP_NEG:
+            regs[d] = E.q_neg(regs[a])
+        elif op == E.OP_ADD:
+            regs[d] = E.q_add(regs[a], regs[b])
+        elif op == E.OP_MUL:
+            regs[d] = E.q_mul(regs[a], regs[b])
+        elif op == E.OP_INV:
+            regs[d] = E.q_inv(regs[a]) if any(regs[a]) else (0, 0, 0)
+        elif op == E.OP_POW:
+            regs[d] = E.q_pow(regs[a], b)
+        elif op == E.OP_STORE:
+            out = regs[a]
+        else:
+            raise AssertionError(op)
+        assert d < E.MAX_REGS
+    return out
+
+
+def direct(expr, x, cols, row, m, challenges=(), hints=(), ccoefs=(), lde_step=1):
+    memo = {}
+
+    def ev(e):
+        if id(e) in memo:
+            return memo[id(e)]
+        k, a = e.kind, e.args
+        if k == "x":
+            v = (x, 0, 0)
+        elif k == "const":
+            v = tuple(a[0])
+        elif k == "chal":
+            v = E._q(challenges[a[0]])
+        elif k == "hint":
+            v = E._q(hints[a[0]])
+        elif k == "ccoef":
+            v = E._q(ccoefs[a[0]])
+        elif k == "trace":
+            t = cols[a[0]][(row + lde_step * a[1]) % m]
+            v = tuple(t) if isinstance(t, tuple) else (t, 0, 0)
+        elif k == "neg":
+            v = E.q_neg(ev(a[0]))
+        elif k == "add":
+            v = E.q_add(ev(a[0]), ev(a[1]))
+        elif k == "mul":
+            v = E.q_mul(ev(a[0]), ev(a[1]))
+        elif k == "div":
+            den = ev(a[1])
+            v = E.q_mul(ev(a[0]), E.q_inv(den) if any(den) else (0, 0, 0))
+        elif k == "pow":
+            v = E.q_pow(ev(a[0]), a[1])
+        else:
+            raise AssertionError(k)
+        memo[id(e)] = v
+        return v
+
+    import sys
+    sys.setrecursionlimit(20000)
+    return ev(expr)
+
+
+def random_columns(rng, nbase, next_, m):
+    cols = [[rng.randrange(P) for _ in range(m)] for _ in range(nbase)]
+    cols += [[tuple(rng.randrange(P) for _ in range(3)) for _ in range(m)] for _ in range(next_)]
+    return cols, [False] * nbase + [True] * next_
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_expressions(seed):
+    rng = random.Random(seed)
+    nbase, next_, m = 4, 2, 8
+    cols, is_q = random_columns(rng, nbase, next_, m)
+    leaves = [E.X()] + [E.Trace(c, o) for c in range(nbase + next_) for o in (0, 1)] + [E.Constant(rng.randrange(P)) for _ in range(3)] \
+        + [E.Constant(tuple(rng.randrange(P) for _ in range(3))), E.Challenge(0), E.Hint(0)]
+    pool = list(leaves)
+    for _ in range(60):
+        a, b = rng.choice(pool), rng.choice(pool)
+        pool.append(rng.choice([lambda: a + b, lambda: a - b, lambda: a * b, lambda: a / (b + E.Constant(1)), lambda: -a,
+                                lambda: a ** rng.randrange(0, 5)])())
+    expr = pool[-1] + pool[-2] * pool[-3] + pool[len(pool) // 2]
+    ch, hi = [tuple(rng.randrange(P) for _ in range(3))], [tuple(rng.randrange(P) for _ in range(3))]
+    plain = E.compile_program(expr, nbase, challenges=ch, hints=hi, lde_step=1, log_ce=3)
+    sym = E.compile_program(expr, nbase, lde_step=1, log_ce=3, symbolic=True).bind(challenges=ch, hints=hi)
+    for row in range(m):
+        x = rng.randrange(1, P)
+        want = direct(expr, x, cols, row, m, ch, hi)
+        assert run_program(plain, x, cols, is_q, row, m) == want
+        assert run_program(sym, x, cols, is_q, row, m) == want
+
+
+@pytest.mark.parametrize("which", ["fib", "perm", "brainfuck"])
+def test_composition_programs_of_the_example_airs(which):
+    """the real compositions: brainfuck's 48 constraints need leaf rematerialisation to fit 48 registers"""
+    rng = random.Random(7)
+    n = 16
+    if which == "fib":
+        cfg, pub, opts = fib.FibAirConfig, 5, fib.OPTIONS
+    elif which == "perm":
+        cfg, pub, opts = perm.PermAirConfig, [], ProofOptions(8, 8, 0, 4, 4)
+    else:
+        cfg, pub, opts, n = bf.BrainfuckAirConfig, bf.BrainfuckClaim("+.", b"", b"\x01"), bf.OPTIONS, 64
+    air = Air(cfg, n, pub, opts)
+    ce = air.ce_blowup_factor
+    m = n * ce
+    cols, is_q = random_columns(rng, cfg.NUM_BASE_COLUMNS, cfg.NUM_EXTENSION_COLUMNS, m)
+    lift = (lambda v: v[0]) if cfg.FQ_IS_FP else (lambda v: v)
+    ch = [lift(tuple(rng.randrange(P) for _ in range(3))) for _ in range(air.num_challenges())]
+    hints = air.gen_hints(ch)
+    cc = [lift(tuple(rng.randrange(P) for _ in range(3))) for _ in range(air.num_composition_constraint_coeffs())]
+    prog = air.composition_program()
+    assert prog.nregs <= E.MAX_REGS and len(prog.bindings) >= len(cc)
+    bound = prog.bind(challenges=ch, hints=hints, ccoefs=cc)
+    substituted = E.compile_program(air.substitute_composition_coeffs(cc), cfg.NUM_BASE_COLUMNS, challenges=ch, hints=hints,
+                                    lde_step=ce, log_ce=m.bit_length() - 1)
+    for row in (0, 1, m - 1, m // 2 + 3):
+        x = rng.randrange(2, P)
+        want = direct(air.composition_constraint, x, cols, row, m, ch, hints, cc, lde_step=ce)
+        assert run_program(bound, x, cols, is_q, row, m) == want
+        assert run_program(substituted, x, cols, is_q, row, m) == want
+
+
+def test_register_pressure_is_reported():
+    # a balanced tree of products of distinct trace cells cannot be evaluated in fewer registers than its depth allows:
+    # interior temporaries are never evicted, so a wide enough expression must raise instead of miscompiling
+    terms = [E.Trace(i % 7, 0) * E.Trace((i + 1) % 7, 1) + E.Constant(i + 1) for i in range(256)]
+    while len(terms) > 1:
+        terms = [terms[i] * terms[i + 1] for i in range(0, len(terms), 2)]
+    prog = E.compile_program(terms[0], 7, log_ce=4)          # Sethi-Ullman order keeps this one small
+    assert prog.nregs <= E.MAX_REGS
+    rng = random.Random(1)
+    cols, is_q = random_columns(rng, 7, 0, 16)
+    assert run_program(prog, 3, cols, is_q, 5, 16) == direct(terms[0], 3, cols, 5, 16)
+
+
+@pytest.mark.parametrize("which", ["fib", "perm"])
+def test_deep_program_symbolic_equals_plain(which):
+    from ministark_b200 import deep
+    rng = random.Random(3)
+    n = 16
+    cfg, pub, opts = (fib.FibAirConfig, 5, fib.OPTIONS) if which == "fib" else (perm.PermAirConfig, [], ProofOptions(8, 8, 0, 4, 4))
+    air = Air(cfg, n, pub, opts)
+    nb, ne, nc = cfg.NUM_BASE_COLUMNS, cfg.NUM_EXTENSION_COLUMNS, air.ce_blowup_factor
+    m = n * opts.lde_blowup_factor
+    cols, is_q = random_columns(rng, nb, ne + nc, m)
+    q3 = lambda: tuple(rng.randrange(P) for _ in range(3))
+    args = air.trace_arguments()
+    z = q3()
+    z_points, z_m = deep.ood_points(z, air.log_n, sorted(set(o for _, o in args)), nc)
+    toods, coods = [q3() for _ in args], [q3() for _ in range(nc)]
+    talphas, calphas, da, db = [q3() for _ in args], [q3() for _ in range(nc)], q3(), q3()
+    plain = E.compile_program(deep.deep_expression(args, nb, ne, nc, z_points, z_m, toods, coods, talphas, calphas, da, db), nb,
+                              log_ce=m.bit_length() - 1)
+    sym, keys = air.deep_program()
+    bound = sym.bind(hints=deep.deep_hint_values(keys, z_points, z_m, toods, coods, talphas, calphas, da, db))
+    for row in (0, 7, m - 1):
+        x = rng.randrange(2, P)
+        assert run_program(bound, x, cols, is_q, row, m) == run_program(plain, x, cols, is_q, row, m)
