@@ -14,7 +14,6 @@ seconds for a 2^24 trace".  See DESIGN.md §Measurement for every key.
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -244,7 +243,6 @@ def workload_config(args):
 
 # ----------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
-    import numpy as np
     import torch
     import torch.distributed as dist
 

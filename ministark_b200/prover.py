@@ -28,7 +28,7 @@ import torch
 from . import FP, FQ3, GENERATOR as GEN_MONT, ONE, Context
 from . import deep
 from . import expr as E
-from .air import Air, domain_generator
+from .air import Air
 from .channel import ProverChannel, PublicCoin, serialize_element
 from .proof import FriProof, LayerProof, MerkleView, Proof, Queries
 
