@@ -167,3 +167,37 @@ def test_brainfuck_vm_with_input():
     assert w[:4] == [0xE4E7F110, 0x15593BD1, 0x1FDD0F50, 0xC47120A3] and w[15] == 0x4E3C50A2
     a, b = bf.test_rng_fq3(2)
     assert a != b and all(0 <= c < bf.P for c in a + b)
+
+
+def test_proof_wire_format_two_implementations_agree():
+    """ministark_b200/proof.py (writer, product) and oracle/stark_oracle.parse_proof (reader, checker) implement the
+    ark-serialize layout of Proof independently: a synthetic proof object round-trips field by field"""
+    from ministark_b200 import proof as PR
+    rng = random.Random(11)
+    dg = lambda: bytes(rng.randrange(256) for _ in range(32))
+    fq = lambda: tuple(rng.randrange(fib.P) for _ in range(3))
+    fp = lambda: rng.randrange(fib.P)
+    view = lambda k: PR.MerkleView([dg() for _ in range(k)], [dg() for _ in range(3)], [dg() for _ in range(2)], 17)
+    for with_ext in (True, False):
+        layers = [PR.LayerProof([fq() for _ in range(16)], view(5), dg()), PR.LayerProof([fq() for _ in range(8)], view(0), dg())]
+        q = PR.Queries([fp() for _ in range(6)], [fq() for _ in range(4)] if with_ext else [], [fq() for _ in range(4)], view(7),
+                       view(6) if with_ext else None, view(4))
+        p = PR.Proof(ProofOptions(19, 16, 20, 16, 16), 1 << 11, dg(), dg() if with_ext else None, dg(), PR.FriProof(layers, [fq(), fq()]),
+                     0xDEADBEEF12345, q, [fq() for _ in range(5)], [fq() for _ in range(2)])
+        b = p.to_bytes()
+        d = SO.parse_proof(b, 3)
+        assert d["options"] == (19, 16, 20, 16, 16) and d["trace_len"] == 2048 and d["pow_nonce"] == 0xDEADBEEF12345
+        assert (d["base_root"], d["ext_root"], d["comp_root"]) == (p.base_trace_commitment, p.extension_trace_commitment,
+                                                                   p.composition_trace_commitment)
+        assert [l["rows"] for l in d["fri_layers"]] == [l.flattenend_rows for l in layers]
+        assert [l["root"] for l in d["fri_layers"]] == [l.commitment for l in layers]
+        assert d["fri_layers"][0]["view"] == dict(nodes=layers[0].merkle_proof.nodes, initial_leaves=layers[0].merkle_proof.initial_leaves,
+                                                  sibling_leaves=layers[0].merkle_proof.sibling_leaves, height=17)
+        assert d["remainder"] == p.fri_proof.remainder_coeffs
+        assert d["base_values"] == [(v, 0, 0) for v in q.base_trace_values] and d["ext_values"] == q.extension_trace_values
+        assert d["comp_values"] == q.composition_trace_values and (d["ext_view"] is None) == (not with_ext)
+        assert d["trace_oods"] == p.execution_trace_ood_evals and d["comp_oods"] == p.composition_trace_ood_evals
+        with pytest.raises(ValueError):
+            SO.parse_proof(b + b"\\x00", 3)
+        with pytest.raises(ValueError):
+            SO.parse_proof(b[:-1], 3)
