@@ -393,7 +393,9 @@ def run_gpu(args):
                 "per_phase_GBps": {k: (alg[k2] / (phase_ms[k] / 1000) / 1e9) for k, k2 in
                                    (("intt", "intt"), ("lde", "lde"), ("constraint_eval", "constraint_eval"))},
                 "merkle_GBps": (alg["leaf_hash"] + alg["merkle_nodes"]) / (phase_ms["merkle"] / 1000) / 1e9,
-                "note": "integer-ALU bound (64-bit modular arithmetic / SHA-256), see DESIGN.md"}
+                "ncu_pipe_utilisation": traffic.get("ncu_pipe_utilisation") if traffic else None,
+                "note": "integer-ALU / issue bound (64-bit modular arithmetic / SHA-256): the HBM fraction is low by "
+                        "construction, see DESIGN.md 5.1 (instruction floor) and the committed ncu summary"}
 
     # ---- CPU baseline: restated reference CPU path on a bounded sample, host cores of this box
     cpu = None

@@ -76,7 +76,15 @@ def main():
     traffic = {"tag": tag, "lde_dram_bytes_per_launch": sum(r[3] + r[4] for r in lde) / max(len(lde), 1),
                "lde_algorithmic_bytes_per_launch": alg * 1e9,
                "source": f"profiles/launches_{tag}.md (ncu dram__bytes_read.sum + dram__bytes_write.sum, full-size step)"}
-    json.dump(traffic, open(os.path.join(ROOT, "profiles", "roofline_traffic.json"), "w"), indent=1)
+    old = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(old):           # keep hand-entered annotations (ncu pipe utilisation of the full-set capture)
+        try:
+            prev = json.load(open(old))
+            for k in prev:
+                traffic.setdefault(k, prev[k])
+        except Exception:
+            pass
+    json.dump(traffic, open(old, "w"), indent=1)
 
     # full-set captures
     want = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
