@@ -48,7 +48,74 @@ class OracleEngine:
         return [o.numpy().tobytes() for o in out]
 
 
-def _worker(rank, world, port, log_n, log_b, ncols, q):
+class PeerOracleEngine(OracleEngine):
+    """OracleEngine + the fused-exchange hooks, with "peer memory" played by POSIX shared memory: ipc_export hands out the
+    segment name, ipc_open attaches to a peer's segment, and addresses are (segment index << 48 | byte offset) so that the
+    block-pointer arithmetic of ShardedCommit.lde_columns is exercised exactly as with device addresses"""
+    peer_scatter = True
+
+    def __init__(self):
+        super().__init__()
+        self.segments = []          # index -> (SharedMemory, numpy uint64 view)
+
+    def _register(self, shm):
+        self.segments.append((shm, np.ndarray(shm.size // 8, dtype=np.uint64, buffer=shm.buf)))
+        return len(self.segments) << 48
+
+    def alloc_exportable(self, shape):
+        from multiprocessing import shared_memory
+        shm = shared_memory.SharedMemory(create=True, size=int(np.prod(shape)) * 8)
+        base = self._register(shm)
+        arr = np.ndarray(shape, dtype=np.int64, buffer=shm.buf)
+        arr[:] = 0
+        self._own = shm
+        return self.torch.from_numpy(arr), base
+
+    def ipc_export(self, ptr):
+        return self._own.name
+
+    def ipc_open(self, handle):
+        from multiprocessing import shared_memory
+        return self._register(shared_memory.SharedMemory(name=handle))
+
+    LOCAL = 1 << 60                 # "address" space of the local LDE buffer
+
+    def ptr(self, buf):
+        self._lde = buf
+        return self.LOCAL
+
+    def sync(self):
+        pass
+
+    def _store(self, addr, words):
+        local = bool(addr & self.LOCAL)
+        addr &= self.LOCAL - 1
+        seg, off = addr >> 48, (addr & ((1 << 48) - 1)) // 8
+        target = self._np(self._lde).reshape(-1) if local else self.segments[seg - 1][1]
+        target[off:off + words.size] = words
+
+    def lde_scatter(self, coeffs, work_ptr, log_n, log_b, ncols, block_ptrs, block_stride, dup_ptrs, dup_stride):
+        n = 1 << log_n
+        lde = self.orc.lde(self._np(coeffs), 1, log_n, log_b, self.orc.generator(), True)
+        for q, (bp, dp) in enumerate(zip(block_ptrs, dup_ptrs)):
+            for c in range(ncols):
+                blk = lde[c, q * n:(q + 1) * n]
+                self._store(bp + c * block_stride * 8, blk)
+                if dp:
+                    self._store(dp + c * dup_stride * 8, blk)
+
+    def close(self):
+        for shm, arr in self.segments:
+            del arr
+        self.segments = []
+        try:
+            self._own.close()
+            self._own.unlink()
+        except Exception:
+            pass
+
+
+def _worker(rank, world, port, log_n, log_b, ncols, q, fused=False):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     from ministark_b200 import parallel
@@ -58,12 +125,22 @@ def _worker(rank, world, port, log_n, log_b, ncols, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         full = orc.rand_matrix(ncols, 1 << log_n, 1, seed=77)          # every rank can regenerate the trace
-        eng = OracleEngine()
-        sc = parallel.ShardedCommit(eng, dist, log_n, log_b, ncols)
+        eng = PeerOracleEngine() if fused else OracleEngine()
+        sc = parallel.ShardedCommit(eng, dist, log_n, log_b, ncols, fused=True if fused else None)
+        assert sc.fused == bool(fused)
         lo, hi = sc.lo, sc.hi
         import torch
-        sc.transform(torch.from_numpy(full[lo:hi].view(np.int64).copy()))
+        local = torch.from_numpy(full[lo:hi].view(np.int64).copy())
+        sc.transform(local)
         root = sc.commit()
+        if fused:
+            sc.transform(local)                      # second round: barrier before the slabs are overwritten
+            assert sc.commit() == root
+            n = 1 << log_n                           # the local copy of block 0 (ce-domain prefix)
+            want = orc.lde(orc.ntt(full[lo:hi], 1, log_n, inverse=True), 1, log_n, log_b, orc.generator(), True)
+            assert np.array_equal(sc.lde.numpy().view(np.uint64)[:, :n], want[:, :n])
+            dist.barrier()
+            eng.close()
         q.put((rank, root))
     finally:
         dist.destroy_process_group()
@@ -77,13 +154,15 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("log_n,log_b,ncols", [(6, 3, 8), (5, 1, 2)])
-def test_sharded_commit_world2_matches_single_tree(orc, log_n, log_b, ncols):
+@pytest.mark.parametrize("log_n,log_b,ncols,fused", [(6, 3, 8, False), (5, 1, 2, False), (6, 3, 8, True), (5, 1, 4, True)])
+def test_sharded_commit_world2_matches_single_tree(orc, log_n, log_b, ncols, fused):
+    """fused=True: the exchange-free path (LDE blocks stored straight into the owners' slabs) with shared memory
+    standing in for CUDA IPC peer memory"""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, log_n, log_b, ncols, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, log_n, log_b, ncols, q, fused)) for r in range(2)]
     for p in procs:
         p.start()
     roots = dict(q.get(timeout=60) for _ in range(2))
