@@ -399,7 +399,7 @@ def run_gpu(args):
 
     # ---- CPU baseline: restated reference CPU path on a bounded sample, host cores of this box
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:      # the CPU baseline is a rank-0, N = 1 measurement
         dt, cval, threads, _ = cpu_sample(args.cpu_log_n, ncols, log_b)
         cpu = {"value": cval, "unit": "field-ops/s", "cores": threads, "kind": "port", "seconds": dt,
                "sample": f"2^{args.cpu_log_n}-row x {ncols}-col trace (1/{1 << (log_n - args.cpu_log_n)} of the rows), all phases, "
