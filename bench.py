@@ -413,7 +413,7 @@ def run_gpu(args):
         "metric": "ntt_field_ops_per_s", "value": value, "unit": "field-ops/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args),
-        "prover_s": ms_per_step / 1000, "phase_ms": phase_ms, "gpu_launches": launches, "clocks": clk,
+        "step_s": ms_per_step / 1000, "phase_ms": phase_ms, "gpu_launches": launches, "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "field-ops/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": ncols * n * 8, "d2h_bytes_per_step": 32 + n * 8},
         "roofline": roofline, "cpu_baseline": cpu, "merkle_root": root.hex() if root else None,
