@@ -110,11 +110,20 @@ class Stark:
         return ex, co, (public_coin.draw(), public_coin.draw())
 
     def prove(self, options, witness, device=0):
-        return GpuProver(device).prove(self, options, witness)
+        """Stark::prove (src/stark.rs:57-63).  The per-device prover (context, stream, compiled AIR programs) is created
+        on first use and reused, like the reference's process-global Planner."""
+        return GpuProver.shared(device).prove(self, options, witness)
 
 
 class GpuProver:
     """owns the device context (one in-order stream) and runs default_prove"""
+    _shared = {}
+
+    @classmethod
+    def shared(cls, device=0):
+        if device not in cls._shared:
+            cls._shared[device] = cls(device)
+        return cls._shared[device]
 
     def __init__(self, device=0):
         self.device = torch.device("cuda", device)

@@ -150,3 +150,16 @@ def test_brainfuck_cycle_burner_proof_bytes_match_cpu_prover(prover, orc):
     want = SO.cpu_prove(claim, opts, trace.base_columns(), mk, ext_builder=trace.build_extension_columns)
     assert got == want
     SO.verify(claim, got, 60, mk)
+
+
+def test_stark_prove_entry_point(orc):
+    """`claim.prove(OPTIONS, trace)` as in examples/fib/main.rs:234-240, through the shared per-device prover"""
+    from oracle import stark_oracle as SO
+    trace, last = fib.gen_trace(8 << 9)
+    claim = fib.FibClaim(last)
+    opts = ProofOptions(12, 4, 4, 8, 16)
+    p1 = claim.prove(opts, trace)
+    p2 = claim.prove(opts, trace)
+    assert p1.to_bytes() == p2.to_bytes()                      # deterministic: smallest-nonce PoW
+    assert GpuProver.shared(0) is GpuProver.shared(0)
+    SO.verify(claim, p1.to_bytes(), 20, air_factory(claim))
