@@ -108,7 +108,7 @@ int ms_lde_batch(ms_ctx *ctx, int field, const void *coeffs, size_t in_stride_el
 int ms_bit_reverse(ms_ctx *ctx, int field, void *data, size_t col_stride_elems, unsigned ncols, unsigned log_n);
 
 /* ---- pointwise stages (gpu/src/stage.rs, 14 stage types; evaluation_shaders.h.metal) ----
- * dst[i] = lhs[i] OP rhs[(i + shift) % n].  dst may alias lhs (the *Assign/*InPlace forms).
+ * dst[i] = lhs[i] OP rhs[(i + shift) % n].  dst may alias lhs (the ...Assign and ...InPlace forms).
  * Unary ops (INV, EXP, NEG, CONVERT) ignore rhs.  exponent is used by EXP / MULPOW. */
 int ms_pointwise(ms_ctx *ctx, int op, int dst_field, void *dst, int lhs_field, const void *lhs,
                  int rhs_field, const void *rhs, size_t n, size_t shift, uint64_t exponent);

