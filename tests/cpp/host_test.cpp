@@ -7,7 +7,7 @@
 #include <iostream>
 #include <sstream>
 
-#include "ministark_host.hpp"
+#include "ministark_examples.hpp"
 
 using namespace mshost;
 
@@ -87,6 +87,38 @@ int main(int argc, char **argv) {
         }
         std::cout << "],\"program\":";
         print_program(air.composition_program(8));
+        std::cout << "}\n";
+    } else if (cmd == "bf") {
+        // host_test bf hello | host_test bf burner a b c | host_test bf src <program> <input>
+        const std::string kind = argv[2];
+        const std::string hello = "++++++++++[>+++++++>++++++++++>+++>+<<<<-]>++.>+.+++++++..+++.>++.<<+++++++++++++++.>.+++.------.--------.";
+        std::string src = kind == "hello" ? hello : (kind == "burner" ? bf::cycle_burner(atoi(argv[3]), atoi(argv[4]), atoi(argv[5])) : std::string(argv[3]));
+        Bytes input;
+        if (kind == "src" && argc > 4) for (const char *c = argv[4]; *c; c++) input.push_back((u8)*c);
+        const bf::VmTrace t = bf::simulate(src, input);
+        Sha256 hs;
+        for (u64 w : t.base) { Bytes le; put_u64_le(le, to_mont(w)); hs.update(le); }
+        std::cout << "{\"n\":" << t.n << ",\"output\":\"" << hex(t.output) << "\",\"base_sha256\":\"" << hex(hs.finish()) << "\"";
+        if (t.n <= 4096) {
+            Air air(bf::air_config(src, input, t.output), t.n, ProofOptions{19, 16, 20, 16, 16});
+            std::cout << ",\"ce_blowup\":" << air.ce_blowup_factor << ",\"nconstraints\":" << air.constraints.size() << ",\"num_challenges\":"
+                      << air.num_challenges() << ",\"num_coeffs\":" << air.num_composition_constraint_coeffs() << ",\"trace_arguments\":[";
+            auto ta = air.trace_arguments();
+            for (size_t i = 0; i < ta.size(); i++) std::cout << (i ? "," : "") << "[" << ta[i].first << "," << ta[i].second << "]";
+            std::cout << "],\"degrees\":[";
+            for (size_t i = 0; i < air.constraints.size(); i++) {
+                auto d = degree(air.g, air.constraints[i].id, t.n - 1);
+                std::cout << (i ? "," : "") << "[" << d.first << "," << d.second << "]";
+            }
+            // hints for fixed challenges (i+1, i+2, i+3)
+            std::vector<Fq> ch;
+            for (u64 i = 0; i < 11; i++) ch.push_back(Fq(i + 1, i + 2, i + 3));
+            std::cout << "],\"hints\":[";
+            auto hints = bf::gen_hints(t.n, src, input, t.output, ch);
+            for (size_t i = 0; i < hints.size(); i++) std::cout << (i ? "," : "") << fq_json(hints[i]);
+            std::cout << "],\"program\":";
+            print_program(air.composition_program(17));
+        }
         std::cout << "}\n";
     } else if (cmd == "expr") {
         Graph g;

@@ -189,3 +189,57 @@ def test_compiler_on_random_expressions(host_test, seed):
     for row in range(m):
         x = rng.randrange(1, P)
         assert run_program(bound, x, cols, is_q, row, m) == direct(expr, x, cols, row, m, ch, hi)
+
+
+@pytest.mark.parametrize("which", ["hello", "burner", "echo"])
+def test_brainfuck_vm_and_air(host_test, which):
+    """include/ministark_examples.hpp: the C++ brainfuck VM produces the same base trace as the Python one, the AIR has
+    the same degrees / blow-up / trace arguments / hints, and its compiled composition evaluates like the Python AIR's"""
+    from ministark_b200.air import degree
+    from ministark_b200.examples import brainfuck as bf
+    if which == "hello":
+        src, inp, args = bf.HELLO_WORLD, b"", ("hello",)
+    elif which == "burner":
+        src, inp, args = bf.cycle_burner(4, 4, 4), b"", ("burner", 4, 4, 4)
+    else:
+        src, inp, args = ",>,<.>.+[-].", b"hi", ("src", ",>,<.>.+[-].", "hi")
+    got = json.loads(host_test("bf", *args))
+    trace, out = bf.simulate(src, inp)
+    n = len(trace)
+    assert got["n"] == n and bytes.fromhex(got["output"]) == out
+    assert got["base_sha256"] == hashlib.sha256(np.ascontiguousarray(trace.base_columns()).tobytes()).hexdigest()
+    claim = bf.BrainfuckClaim(src, inp, out)
+    air = Air(bf.BrainfuckAirConfig, n, claim, bf.OPTIONS)
+    assert (got["ce_blowup"], got["nconstraints"], got["num_challenges"], got["num_coeffs"]) == \
+        (air.ce_blowup_factor, len(air.constraints), air.num_challenges(), air.num_composition_constraint_coeffs())
+    assert [tuple(t) for t in got["trace_arguments"]] == air.trace_arguments()
+    assert [tuple(d) for d in got["degrees"]] == [degree(c, n - 1) for c in air.constraints]
+    ch = [(i + 1, i + 2, i + 3) for i in range(11)]
+    hints = air.gen_hints(ch)
+    assert [tuple(h) for h in got["hints"]] == [tuple(h) for h in hints]
+    prog = Prog(got["program"])
+    assert prog.nregs <= E.MAX_REGS
+    rng = random.Random(5)
+    m = n * air.ce_blowup_factor
+    pick = [0, 1, 17, m - 1, m // 2]
+    nb, ne = 17, 9
+    lazy = {}                   # 26 columns x 32768 rows: sampled lazily, only the cells the constraints touch
+
+    class Col:
+        def __init__(self, c, is_q):
+            self.c, self.q = c, is_q
+
+        def __getitem__(self, r):
+            key = (self.c, r)
+            if key not in lazy:
+                lazy[key] = tuple(rng.randrange(P) for _ in range(3)) if self.q else rng.randrange(P)
+            return lazy[key]
+
+    cols = [Col(c, False) for c in range(nb)] + [Col(nb + c, True) for c in range(ne)]
+    is_q = [False] * nb + [True] * ne
+    cc = [tuple(rng.randrange(P) for _ in range(3)) for _ in range(air.num_composition_constraint_coeffs())]
+    bound = prog.bind(challenges=ch, hints=hints, ccoefs=cc)
+    for row in pick:
+        x = rng.randrange(2, P)
+        want = direct(air.composition_constraint, x, cols, row, m, ch, hints, cc, lde_step=air.ce_blowup_factor)
+        assert run_program(bound, x, cols, is_q, row, m) == want
