@@ -18,18 +18,41 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.xfail(reason="first device run of the C++ driver (written after the round's GPU budget was used up)", strict=False)
-@pytest.mark.parametrize("log_rows,opts", [(7, (16, 4, 4, 8, 16)), (12, (32, 4, 8, 8, 64))])
-def test_cpp_prover_bytes_equal_python_prover(tmp_path, log_rows, opts):
+def _build(tmp_path):
     exe = tmp_path / "prover_test"
     lib = os.path.join(ROOT, "ministark_b200")
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"),
                            os.path.join(ROOT, "tests", "cpp", "prover_test.cpp"), "-o", str(exe),
                            "-L", lib, "-lministark_b200", f"-Wl,-rpath,{lib}"])
-    out = subprocess.run([str(exe), str(log_rows)] + [str(o) for o in opts], capture_output=True, text=True, timeout=600)
+    return exe
+
+
+@pytest.mark.xfail(reason="first device run of the C++ driver (written after the round's GPU budget was used up)", strict=False)
+@pytest.mark.parametrize("log_rows,opts", [(7, (16, 4, 4, 8, 16)), (12, (32, 4, 8, 8, 64))])
+def test_cpp_prover_bytes_equal_python_prover(tmp_path, log_rows, opts):
+    exe = _build(tmp_path)
+    out = subprocess.run([str(exe), "fib", str(log_rows)] + [str(o) for o in opts], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr
     last, hexbytes = out.stdout.split()
     trace, want_last = fib.gen_trace(8 << log_rows)
     assert int(last) == want_last
     want = GpuProver.shared(0).prove(fib.FibClaim(want_last), ProofOptions(*opts), trace).to_bytes()
+    assert bytes.fromhex(hexbytes) == want
+
+
+@pytest.mark.xfail(reason="first device run of the C++ driver (written after the round's GPU budget was used up)", strict=False)
+@pytest.mark.parametrize("which,opts", [("hello", (19, 16, 20, 16, 16)), ("burner:4:4:4", (16, 16, 6, 8, 8))])
+def test_cpp_prover_brainfuck_bytes_equal_python_prover(tmp_path, which, opts):
+    """extension columns built on the device by the C++ twin of _device_extension (evaluator + ms_scan_affine)"""
+    from ministark_b200.examples import brainfuck as bf
+    exe = _build(tmp_path)
+    ii, mi = bf.test_rng_fq3(2)
+    out = subprocess.run([str(exe), "bf", which] + [str(o) for o in opts] + [str(v) for v in ii + mi], capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stderr
+    output_hex, hexbytes = out.stdout.split()
+    src = bf.HELLO_WORLD if which == "hello" else bf.cycle_burner(*[int(v) for v in which.split(":")[1:]])
+    trace, output = bf.simulate(src)
+    assert bytes.fromhex(output_hex[len("out:"):]) == output
+    want = GpuProver.shared(0).prove(bf.BrainfuckClaim(src, b"", output), ProofOptions(*opts), trace).to_bytes()
     assert bytes.fromhex(hexbytes) == want
