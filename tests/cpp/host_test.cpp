@@ -8,6 +8,7 @@
 #include <sstream>
 
 #include "ministark_examples.hpp"
+#include "ministark_verifier.hpp"
 
 using namespace mshost;
 
@@ -120,6 +121,32 @@ int main(int argc, char **argv) {
             print_program(air.composition_program(17));
         }
         std::cout << "}\n";
+    } else if (cmd == "verify") {
+        // host_test verify fib <claim> <bits>            proof hex on stdin
+        // host_test verify bf <source> <output hex> <bits>
+        std::string hexproof;
+        std::cin >> hexproof;
+        const Bytes proof = unhex(hexproof);
+        try {
+            std::vector<u64> pos;
+            if (std::string(argv[2]) == "fib") {
+                pos = verify(fib_air_config(), proof, {Fq(strtoull(argv[3], nullptr, 10))}, {}, (u32)atoi(argv[4]));
+            } else {
+                const std::string src = argv[3];
+                const Bytes output = unhex(argv[4]);
+                pos = verify(bf::air_config(src, {}, output), proof, {}, [&] {
+                    Bytes o;
+                    put_u64_le(o, src.size()); o.insert(o.end(), src.begin(), src.end());
+                    put_u64_le(o, 0);
+                    put_u64_le(o, output.size()); o.insert(o.end(), output.begin(), output.end());
+                    return o; }(), (u32)atoi(argv[5]));
+            }
+            std::cout << "ok";
+            for (u64 p : pos) std::cout << " " << p;
+            std::cout << "\n";
+        } catch (const std::exception &e) {
+            std::cout << "error: " << e.what() << "\n";
+        }
     } else if (cmd == "expr") {
         Graph g;
         std::vector<Expr> st;

@@ -243,3 +243,44 @@ def test_brainfuck_vm_and_air(host_test, which):
         x = rng.randrange(2, P)
         want = direct(air.composition_constraint, x, cols, row, m, ch, hints, cc, lde_step=air.ce_blowup_factor)
         assert run_program(bound, x, cols, is_q, row, m) == want
+
+
+def test_cpp_verifier_accepts_and_rejects_like_the_python_restatement(host_test, orc):
+    """include/ministark_verifier.hpp (default_verify as a C++ library): accepts the CPU prover's
+    proofs for examples/fib and examples/brainfuck with the same query positions as the Python restatement, refuses a wrong
+    claim, too little security, and every sampled single-bit corruption (which the Python verifier refuses too)"""
+    from ministark_b200.examples import brainfuck as bf
+    from oracle import stark_oracle as SO
+    rng = random.Random(77)
+
+    def cpp(kind, proof, *args):
+        return host_test("verify", kind, *args, stdin=proof.hex()).strip()
+
+    # ---- fib
+    opts = (32, 4, 8, 8, 64)
+    trace, last = fib.gen_trace(8 << 7)
+    claim = fib.FibClaim(last)
+    mk = lambda n, o: Air(claim.AirConfig, n, claim.get_public_inputs(), ProofOptions(*o))
+    proof = SO.cpu_prove(claim, opts, trace.base_columns(), mk)
+    art = SO.verify(claim, proof, 30, mk)
+    assert cpp("fib", proof, last, 30) == "ok " + " ".join(str(p) for p in art["query_positions"])
+    assert cpp("fib", proof, (last + 1) % P, 30).startswith("error: constraint evaluations at the out-of-domain point")
+    assert cpp("fib", proof, last, 100).startswith("error: proof params do not satisfy security")
+    for _ in range(30):
+        b = bytearray(proof)
+        b[rng.randrange(5, len(b))] ^= 1 << rng.randrange(8)
+        with pytest.raises((SO.VerificationError, ValueError)):
+            SO.verify(claim, bytes(b), 30, mk)
+        assert cpp("fib", bytes(b), last, 30).startswith("error:")
+    # ---- brainfuck hello world (Fq3, extension columns, ce_blowup 16, 2 FRI layers of folding factor 16)
+    btrace, out = bf.simulate(bf.HELLO_WORLD)
+    bclaim = bf.BrainfuckClaim(bf.HELLO_WORLD, b"", out)
+    bmk = lambda n, o: Air(bclaim.AirConfig, n, bclaim, ProofOptions(*o))
+    bproof = SO.cpu_prove(bclaim, (19, 16, 20, 16, 16), btrace.base_columns(), bmk, ext_builder=btrace.build_extension_columns)
+    bart = SO.verify(bclaim, bproof, 96, bmk)
+    assert cpp("bf", bproof, bf.HELLO_WORLD, out.hex(), 96) == "ok " + " ".join(str(p) for p in bart["query_positions"])
+    assert cpp("bf", bproof, bf.HELLO_WORLD, b"Hello World?".hex(), 96).startswith("error:")
+    for _ in range(12):
+        b = bytearray(bproof)
+        b[rng.randrange(5, len(b))] ^= 1 << rng.randrange(8)
+        assert cpp("bf", bytes(b), bf.HELLO_WORLD, out.hex(), 96).startswith("error:")
