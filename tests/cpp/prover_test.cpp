@@ -6,6 +6,7 @@
 #include <iostream>
 
 #include "ministark_prover.hpp"
+#include "ministark_verifier.hpp"
 
 using namespace mshost;
 
@@ -27,6 +28,7 @@ int main(int argc, char **argv) {
             std::vector<u64> trace;
             const u64 last = fib_gen_trace(n, trace);          // examples/fib/main.rs:175-222
             const Proof proof = prover.prove(fib_air_config(), opts, trace.data(), n, {Fq(last)});
+            verify(fib_air_config(), proof.to_bytes(1), {Fq(last)}, {}, 10);        // the C++ verifier accepts its own prover's proof
             std::cout << last << " " << hex(proof.to_bytes(1)) << "\n";
         } else {
             if (argc < 14) { fprintf(stderr, "bf needs the two initial values\n"); return 2; }
@@ -43,6 +45,7 @@ int main(int argc, char **argv) {
                                              [&](ms_ctx *ctx, const u64 *base_dev, u64, const std::vector<Fq> &ch) {
                                                  return bf::device_extension(ctx, t, base_dev, ch, ii, mi);
                                              });
+            verify(bf::air_config(src, {}, t.output), proof.to_bytes(3), {}, bf::claim_bytes(src, {}, t.output), 10);
             std::cout << "out:" << hex(t.output) << " " << hex(proof.to_bytes(3)) << "\n";
         }
     } catch (const std::exception &e) {
