@@ -198,6 +198,25 @@ def full_prove_sample(log_rows=21):
             "verified": True, "launches": prover.ctx.launches}
 
 
+def cpu_full_prove_sample(log_rows):
+    """default_prove in the reference's own formulation on the host cores (oracle/stark_oracle.cpu_prove: per-column
+    transforms, coefficient-form DEEP, apply_drp through two transforms, CPU Merkle), examples/fib, checked by the
+    restated verifier — the CPU counterpart of full_prove_sample at a size that stays within the time budget"""
+    import time
+    from ministark_b200.air import Air, ProofOptions
+    from ministark_b200.examples import fib
+    from oracle import stark_oracle
+    trace, last = fib.gen_trace(8 << log_rows)
+    claim = fib.FibClaim(last)
+    mk = lambda n, o: Air(claim.AirConfig, n, claim.get_public_inputs(), ProofOptions(*o))
+    t = time.perf_counter()
+    proof = stark_oracle.cpu_prove(claim, (32, 4, 8, 8, 64), trace.base_columns(), mk)
+    dt = time.perf_counter() - t
+    stark_oracle.verify(claim, proof, fib.SECURITY_LEVEL, mk)
+    return {"workload": f"examples/fib: 2^{log_rows} rows x 8 Fp columns, ProofOptions(32, 4, 8, 8, 64), CPU restatement of default_prove",
+            "seconds": dt, "proof_bytes": len(proof), "verified": True}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -223,6 +242,7 @@ def run_reference(args):
         "config": workload_config(args),
         "cpu_baseline": {"value": val, "unit": "field-ops/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "field-ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "full_prove": None if args.no_prover else cpu_full_prove_sample(args.cpu_prove_log_rows),
         "wall_s": time.perf_counter() - t0,
     }))
 
@@ -436,6 +456,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="resident steps only (for ncu captures)")
     ap.add_argument("--no-prover", action="store_true", help="skip the examples/fib full-prove sample")
+    ap.add_argument("--cpu-prove-log-rows", type=int, default=18, help="--impl reference: rows of the CPU full-prove sample")
     ap.add_argument("--no-fused-exchange", action="store_true", help="N > 1: LDE then NCCL all-to-all instead of the fused scatter")
     args = ap.parse_args()
     args.cpu_log_n = min(args.cpu_log_n, args.log_n)
