@@ -103,6 +103,10 @@ class Context:
     def sync(self):
         self._ck(self.lib.ms_ctx_sync(self.h))
 
+    def set_option(self, name, value):
+        """kernel tuning / A-B switches (ms_set_option), e.g. ("ntt_tma", 0) selects the one-tile-per-CTA NTT passes"""
+        self._ck(self.lib.ms_set_option(self.h, name.encode(), int(value)))
+
     @property
     def launches(self):
         return int(self.lib.ms_launch_count(self.h))

@@ -25,6 +25,7 @@ _SIGS = {
     "ms_last_error": (C.c_char_p, [vp]),
     "ms_version": (C.c_char_p, []),
     "ms_launch_count": (u64, [vp]),
+    "ms_set_option": (ci, [vp, C.c_char_p, C.c_int64]),
     "ms_alloc_device": (ci, [vp, sz, C.POINTER(vp)]),
     "ms_alloc_host_pinned": (ci, [vp, sz, C.POINTER(vp)]),
     "ms_free": (ci, [vp, vp]),

@@ -148,7 +148,6 @@ int ms_ctx_create(int device, ms_ctx **out) {
         return MS_ERR_CUDA;
     }
     c->stream = c->own_stream;
-    msntt::upload_constants();
     // omega_4096^e tables, forward and inverse
     {
         std::vector<u64> h(2 * 4096);
@@ -203,6 +202,23 @@ int ms_ctx_sync(ms_ctx *c) {
     if (!c) return MS_ERR_INVALID;
     MS_CUDA(c, cudaStreamSynchronize(c->stream));
     return MS_OK;
+}
+
+// tuning / A-B switches (process-wide): "ntt_tma" 0|1, "ntt_tma_groups" 2|3, "ntt_tma_stages" 3..8
+int ms_set_option(ms_ctx *c, const char *name, int64_t value) {
+    if (!name) return MS_ERR_INVALID;
+    if (!strcmp(name, "ntt_tma")) { msntt::tma_configure(value ? 1 : 0, 0, 0); return MS_OK; }
+    if (!strcmp(name, "ntt_tma_groups")) {
+        if (value != 2 && value != 3) return fail(c, MS_ERR_INVALID, "ntt_tma_groups must be 2 or 3");
+        msntt::tma_configure(-1, (int)value, 0);
+        return MS_OK;
+    }
+    if (!strcmp(name, "ntt_tma_stages")) {
+        if (value < 3 || value > 8) return fail(c, MS_ERR_INVALID, "ntt_tma_stages must be in [3, 8]");
+        msntt::tma_configure(-1, 0, (int)value);
+        return MS_OK;
+    }
+    return fail(c, MS_ERR_INVALID, "unknown option %s", name);
 }
 
 const char *ms_last_error(ms_ctx *c) { return c ? c->err.c_str() : "null context"; }

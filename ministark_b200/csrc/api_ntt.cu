@@ -343,6 +343,11 @@ int ntt_run(ms_ctx *c, NttPlanDev &P, const u64 *in, size_t in_cs, u64 *out, siz
                 p.out_col_stride = (k == m - 1) ? out_cs : col_words;
             }
             p.nbatch = nc * P.lanes * P.ncos;
+            if (msntt::launch_pass_tma(p, P.tb, P.job.inverse, pin, pout, P.ntiles[k], nc, c->stream)) {
+                c->launches++;
+                MS_CHECK_LAUNCH(c);
+                continue;
+            }
             msntt::launch_pass(p, P.tb, P.job.inverse, pin, pout, P.ntiles[k], p.nbatch, c->stream);
             c->launches++;
             MS_CHECK_LAUNCH(c);

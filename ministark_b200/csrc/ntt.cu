@@ -32,8 +32,6 @@ namespace msntt {
 
 using namespace gl;
 
-void upload_constants() {}
-
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ u32 brev_rt(u32 k, int bits) { return bits ? (__brev(k) >> (32 - bits)) : 0; }
 

@@ -85,7 +85,11 @@ void launch_pass(const PassParams &p, const Tables &t, bool inverse, const u64 *
 void launch_naive(const u64 *in, u64 in_stride_words, u64 *out, u64 out_stride_words, unsigned log_n, unsigned estride,
                   unsigned lanes, unsigned ncols, bool inverse, u64 root_mont, u64 offset_mont, cudaStream_t stream);
 
-void upload_constants();
+// persistent TMA pipeline (ntt_tma.cu) for the 256 x 16 tile passes of Fp transforms; false = shape not covered, nothing
+// launched.  tma_configure: enabled (0/1, -1 keeps), consumer groups per CTA (2/3), cap on shared-memory stages.
+bool launch_pass_tma(const PassParams &p, const Tables &t, bool inverse, const u64 *in, u64 *out, unsigned ntiles,
+                     unsigned ncols, cudaStream_t stream);
+void tma_configure(int enabled, int groups, int max_stages);
 // table builders (device kernels): dst[i] = lookup2(lo, hi, hi_len, i) and the outer-twiddle table
 void build_pow_table(u64 *dst, u64 count, const u64 *lo, const u64 *hi, u32 hi_len, cudaStream_t stream);
 void build_outer_table(u64 *dst, u64 R, u64 S, u64 mult, u64 n_mask, const u64 *lo, const u64 *hi, u32 hi_len,
