@@ -10,13 +10,13 @@
 //                    of the next tiles into a ring of 32 KiB shared-memory stages, each guarded by an mbarrier, and
 //                    drains finished stages with TMA stores (bulk async-groups).  No thread computes an address of
 //                    global memory or touches LDG/STG: the ALU pipe is left to the butterflies.
-//   warps 1..8G      consumers.  A tile is split by lane pairs: each warp owns 2 of the 16 lanes, i.e. a 256 x 2
-//                    sub-tile, and runs both radix-16 steps of its 256-point sub-NTTs on it.  With the 128-byte
-//                    swizzle the 16 threads that exchange data between the two steps sit in ONE warp and every
-//                    shared-memory access of either step is conflict free (2 wavefronts per 64-bit warp access, the
-//                    minimum), so the only synchronisation inside a tile is __syncwarp(): no CTA barrier, no padding,
-//                    no second copy.  G groups of 8 warps work on G different tiles, so one group's exchange
-//                    latency is covered by the others' arithmetic.
+//   warps 1..8G      consumers: G groups of 8 warps, each group works on its own tile (256 threads x 16 elements), in
+//                    place in the stage.  Strided tiles: a half warp spans the 16 lanes of one tile row, so both
+//                    radix-16 steps touch whole 128-byte rows — conflict free, no padding, no second copy — and the
+//                    exchange between the steps costs one named barrier of the group.  Contiguous tiles: the 16
+//                    threads that exchange sit in one half warp (__syncwarp only) and the 128-byte swizzle makes both
+//                    the stride-16 step and the whole-row 128-bit step conflict free.  One group's exchange and
+//                    mbarrier waits are covered by the other groups' arithmetic.
 //
 //   pass kinds      strided   rows S words apart (S = 2^16 or 2^8), lanes contiguous: box 16 x 256 of the
 //                             (S, 256, blocks*cosets, columns) tensor.  Inter-pass twiddles w_{RS}^(i_R * lower) come
@@ -125,12 +125,19 @@ __device__ __forceinline__ void inner_twiddles(u64 (&x)[16], const u64 *__restri
     });
 }
 
-// One warp's share (lanes c, c+1 of the tile; 16 threads each) of a strided-pass tile, in place.
+__device__ __forceinline__ void group_sync(const u32 g) { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); }
+
+// One thread's share of a strided-pass tile, in place.  tg = thread index inside the consumer group (256 threads): the
+// 16 lanes of a half warp are the 16 lanes of ONE tile row, so every access below reads or writes whole 128-byte rows
+// (2 rows per warp access = 2 wavefronts, the minimum) whatever the row: both radix-16 steps are conflict free.  (Lanes
+// running over the rows instead would make the exchange warp-local, but rows 16 b + K share row % 8 — the only input of
+// the 128-byte swizzle — and step 2 would serialise 16-fold.)  The exchange between the steps spans the group: one
+// named barrier.
 template <bool INV, bool BITREV, bool HAS_PRE>
 __device__ __forceinline__ void tile_strided(u64 *__restrict__ tile, const u64 *__restrict__ tw, const u64 *__restrict__ pre,
-                                             const u64 *__restrict__ t16, const u32 lane, const u32 wp) {
-    const u32 c = 2 * wp + (lane >> 4);
-    const u32 a = lane & 15;
+                                             const u64 *__restrict__ t16, const u32 tg, const u32 g) {
+    const u32 c = tg & 15;
+    const u32 a = tg >> 4;
     u64 x[16];
     {   // step 1: rows a + 16 K (high digit), outputs kappa1 -> rows a + 16 * (brev) kappa1
         const u32 o1 = swz(a, c);   // (a + 16 K) % 8 == a % 8: one swizzle term for all K
@@ -140,7 +147,7 @@ __device__ __forceinline__ void tile_strided(u64 *__restrict__ tile, const u64 *
         inner_twiddles<INV>(x, t16, a);
         static_for<0, 16>([&](auto Q) { tile[o1 + 256 * (u32)Q] = BITREV ? x[Q] : x[brev_c(decltype(Q)::value, 4)]; });
     }
-    __syncwarp();
+    group_sync(g);
     {   // step 2: rows 16 b + K (low digit); i_R = kappa1 + 16 kappa2
         const u32 b = a;
         const u32 o2 = 256 * b + c;   // row 16 b + K has swizzle term K % 8: offset = (o2 ^ ((K & 7) << 1)) + 16 K
@@ -155,7 +162,7 @@ __device__ __forceinline__ void tile_strided(u64 *__restrict__ tile, const u64 *
         if constexpr (BITREV) {
             static_for<0, 16>([&](auto Q) { tile[(o2 ^ (((u32)Q & 7) << 1)) + 16 * (u32)Q] = x[Q]; });
         } else {
-            __syncwarp();   // rows b + 16 kappa2 belong to other threads' inputs: everyone has read before anyone writes
+            group_sync(g);   // rows b + 16 kappa2 are other threads' inputs: everyone has read before anyone writes
             const u32 on = swz(b, c);
             static_for<0, 16>([&](auto KAP) { tile[on + 256 * (u32)KAP] = x[brev_c(decltype(KAP)::value, 4)]; });
         }
@@ -363,7 +370,7 @@ ntt_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
                 mbar_wait(full_bar(s), k & 1);
                 u64 *tile = stages + (size_t)s * kTileWords;
                 if constexpr (TYPE == 0)
-                    tile_strided<INV, BITREV, HAS_PRE>(tile, tw_s, pre_s + slot * kTileWords, t16, lane, wp);
+                    tile_strided<INV, BITREV, HAS_PRE>(tile, tw_s, pre_s + slot * kTileWords, t16, wp * 32 + lane, g);
                 else
                     tile_contig<INV>(tile, t16, lane, wp);
                 fence_proxy_async();   // generic-proxy writes of the tile before the async-proxy (TMA store) reads

@@ -26,10 +26,17 @@ def emit(**kw):
     print(json.dumps(kw), flush=True)
 
 
+def new_ctx():
+    """a dedicated torch stream (the legacy default stream's handle is NULL, which ms_ctx_set_stream reads as "own stream")"""
+    global _STREAM
+    _STREAM = torch.cuda.Stream()
+    torch.cuda.set_stream(_STREAM)
+    return ms.Context(0, stream=_STREAM.cuda_stream)
+
+
 def check():
     from oracle import oracle as orc
-    ctx = ms.Context(0)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx = new_ctx()
     ok = True
     # 2^16: passes [8, 8] -> strided (TMA) + contiguous (TMA) for the LDE; strided natural + transposing (old) for NTT
     for log_n, log_b, ncols in [(16, 3, 8), (16, 2, 16), (16, 0, 64)]:
@@ -117,8 +124,7 @@ def timeit(fn, reps=3):
 
 
 def bench():
-    ctx = ms.Context(0)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx = new_ctx()
     log_n, log_b, ncols = 24, 3, 32
     n = 1 << log_n
     tr = torch.empty((ncols, n), dtype=torch.int64, device="cuda")
