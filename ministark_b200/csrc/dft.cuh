@@ -10,13 +10,40 @@ using namespace gl;
 
 // omega_16^k, k = 0..7, Montgomery form; forward and inverse.
 template <bool INV>
-__device__ __forceinline__ constexpr u64 w16(int k) {
+__host__ __device__ __forceinline__ constexpr u64 w16(int k) {
     constexpr u64 F[8] = {0x00000000FFFFFFFFULL, 0x0000000010000000ULL, 0xFEFFFFFF01000001ULL, 0xFFEFFFFF00000001ULL,
                           0xFFFFFFFEFFFF0001ULL, 0x00000FFFFFFFF000ULL, 0x0000010000000000ULL, 0x0000000000000010ULL};
     constexpr u64 I[8] = {0x00000000FFFFFFFFULL, 0xFFFFFFFEFFFFFFF1ULL, 0xFFFFFEFF00000001ULL, 0xFFFFEFFF00001001ULL,
                           0x0000000000010000ULL, 0x0010000000000000ULL, 0x00FFFFFFFF000000ULL, 0xFFFFFFFEF0000001ULL};
     return INV ? I[k] : F[k];
 }
+
+// The same constants as signed powers of two: Montgomery word of omega_16^k = (neg ? p - 2^m : 2^m).  A butterfly then
+// needs no multiplication: t = mul_pow2<m>(v) (a 128-bit shift + the Montgomery reduction) and, for a negative constant,
+// the sum and the difference swap places.
+struct W16Shift {
+    int m;
+    bool neg;
+};
+template <bool INV>
+__host__ __device__ constexpr W16Shift w16_shift(int k) {
+    constexpr W16Shift F[8] = {{0, false}, {28, false}, {88, true}, {52, true}, {16, true}, {76, false}, {40, false}, {4, false}};
+    constexpr W16Shift I[8] = {{0, false}, {4, true}, {40, true}, {76, true}, {16, false}, {52, false}, {88, false}, {28, true}};
+    return INV ? I[k] : F[k];
+}
+__host__ __device__ constexpr u64 pow2_mod_p(int m) {   // 2^m mod p, m < 96
+    return m < 64 ? (1ULL << m) : ((1ULL << (m - 32)) - (1ULL << (m - 64)));   // 2^64 = 2^32 - 1
+}
+template <bool INV, int K>
+__host__ __device__ constexpr bool w16_shift_ok() {
+    constexpr W16Shift s = w16_shift<INV>(K);
+    constexpr u64 v = pow2_mod_p(s.m);
+    return (s.neg ? P - v : v) == w16<INV>(K);
+}
+static_assert(w16_shift_ok<false, 1>() && w16_shift_ok<false, 2>() && w16_shift_ok<false, 3>() && w16_shift_ok<false, 4>() &&
+              w16_shift_ok<false, 5>() && w16_shift_ok<false, 6>() && w16_shift_ok<false, 7>(), "forward 16th roots");
+static_assert(w16_shift_ok<true, 1>() && w16_shift_ok<true, 2>() && w16_shift_ok<true, 3>() && w16_shift_ok<true, 4>() &&
+              w16_shift_ok<true, 5>() && w16_shift_ok<true, 6>() && w16_shift_ok<true, 7>(), "inverse 16th roots");
 
 // compile-time loop: f(IC<I>) for I in [0, N)
 template <int V>
@@ -58,10 +85,22 @@ struct Bfly {
                     x[A + span] = sub_ll(u, v);
                 }
             } else {
+#ifdef MS_DFT_CONST_MUL      // A/B: the constants through the generic multiplication
                 constexpr u64 w = w16<INV>(j * (16 >> S));
                 const u64 t = mul(v, w);
                 x[A] = add_lc(u, t);
                 x[A + span] = sub_lc(u, t);
+#else
+                constexpr W16Shift sh = w16_shift<INV>(j * (16 >> S));
+                const u64 t = mul_pow2<sh.m>(v);
+                if constexpr (sh.neg) {          // u + (-t), u - (-t)
+                    x[A] = sub_lc(u, t);
+                    x[A + span] = add_lc(u, t);
+                } else {
+                    x[A] = add_lc(u, t);
+                    x[A + span] = sub_lc(u, t);
+                }
+#endif
             }
         }
         if constexpr (A + 1 < (1 << B))

@@ -154,6 +154,21 @@ GL_HD u64 mul(u64 a, u64 b) {
     return mont_reduce((u64)(x >> 64), (u64)x);
 #endif
 }
+// x * W * 2^-64 mod p for a twiddle whose Montgomery word W is the power of two 2^M (the 16th roots of unity all are,
+// up to sign: dft.cuh) — the 128-bit product is a shift, so no multiplication instruction is spent; same canonical
+// result as mul(x, 2^M mod p).  x may be any u64.
+template <int M>
+GL_HD u64 mul_pow2(u64 x) {
+    static_assert(M > 0 && M < 96, "shift out of range");
+    if constexpr (M < 64) {
+        return mont_reduce(x >> (64 - M), x << M);       // x * 2^M < p * 2^64: canonical
+    } else {
+        // 2^M * 2^-64 = 2^k, k = M - 64 < 32:  x * 2^k = lo + hi * 2^64 = lo + hi * eps  (hi < 2^k, so hi * eps < p)
+        constexpr int k = M - 64;
+        const u64 lo = x << k, hi = x >> (64 - k);
+        return canon(add_lc(lo, (hi << 32) - hi));
+    }
+}
 GL_HD u64 sqr(u64 a) { return mul(a, a); }
 GL_HD u64 to_mont(u64 x_canon) { return mul(x_canon, R2); }
 GL_HD u64 from_mont(u64 w) { return mul(w, 1); }
