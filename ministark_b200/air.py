@@ -6,7 +6,7 @@
     composition constraint            src/air.rs:50-82
 
 Constraints are `ministark_b200.expr.Expr` DAGs over the leaves X | Constant | Challenge(i) | Hint(i) |
-Trace(column, offset) (periodic columns are not supported; no BASELINE AIR uses them) plus, inside the
+Trace(column, offset) | Periodic(coeffs, interval_size) plus, inside the
 composition constraint only, CompositionCoeff(i) — the verifier randomness that is substituted as
 constants once the channel has produced it (src/air.rs:96-101).
 
@@ -98,6 +98,9 @@ def degree(expr, trace_degree):
             d = (trace_degree, 0)
         elif k == "x":
             d = (1, 0)
+        elif k == "periodic":
+            # PeriodicColumn::degree (src/constraints.rs:131-138): (len(coeffs) - 1) * (trace_len / interval_size)
+            d = ((len(a[0]) - 1) * ((trace_degree + 1) // a[1]), 0)
         elif k == "neg":
             d = memo[id(a[0])]
         elif k == "add":

@@ -183,6 +183,8 @@ int ms_ctx_destroy(ms_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->plans.clear();
+    for (auto &t : c->tw_tables) cudaFree(t.second);
+    c->tw_tables.clear();
     for (auto &s : c->scratch)
         if (s.ptr) cudaFree(s.ptr);
     if (c->t4096[0]) cudaFree(c->t4096[0]);
@@ -216,6 +218,12 @@ int ms_set_option(ms_ctx *c, const char *name, int64_t value) {
     if (!strcmp(name, "ntt_tma_stages")) {
         if (value < 3 || value > 8) return fail(c, MS_ERR_INVALID, "ntt_tma_stages must be in [3, 8]");
         msntt::tma_configure(-1, 0, (int)value);
+        return MS_OK;
+    }
+    if (!strcmp(name, "drop_plans")) {   // free the cached NTT plans and their big tables (rebuilt on demand)
+        if (!c) return MS_ERR_INVALID;
+        cudaSetDevice(c->device);
+        ms::ntt_drop_plans(c);
         return MS_OK;
     }
     return fail(c, MS_ERR_INVALID, "unknown option %s", name);

@@ -255,14 +255,48 @@ int ntt_get_plan(ms_ctx *c, const NttJob &job, std::shared_ptr<NttPlanDev> *out)
     return MS_OK;
 }
 
+// Two-level table of g_n^e only (what the FRI fold, the evaluator's X leaf and the scans need): a few KiB per size,
+// cached per context — NOT a full transform plan, whose inter-pass and scale tables run to hundreds of MiB.
 int ntt_plan_tables(ms_ctx *c, unsigned log_n, const u64 **tw_lo, const u64 **tw_hi, u32 *hi_len) {
-    NttJob job{MS_FIELD_FP, log_n, false, false, 0, gl::ONE};
-    std::shared_ptr<NttPlanDev> P;
-    if (int rc = ntt_get_plan(c, job, &P)) return rc;
-    *tw_lo = P->tb.tw_lo;
-    *tw_hi = P->tb.tw_hi;
-    *hi_len = (u32)std::max<u64>(1, P->N >> 12);
+    const u32 hl = (u32)std::max<u64>(1, (1ull << log_n) >> 12);
+    auto it = c->tw_tables.find(log_n);
+    if (it == c->tw_tables.end()) {
+        // reuse a full plan's tables when one exists already
+        auto key = std::make_tuple((int)MS_FIELD_FP, log_n, 0, (uint64_t)gl::ONE, 0u, 0);
+        auto pit = c->plans.find(key);
+        if (pit != c->plans.end()) {
+            *tw_lo = pit->second->tb.tw_lo;
+            *tw_hi = pit->second->tb.tw_hi;
+            *hi_len = hl;
+            return MS_OK;
+        }
+        const size_t lo_len = 4096;
+        std::vector<u64> h(lo_len + hl);
+        const u64 root = root_of_unity(log_n);
+        u64 a = gl::ONE;
+        for (size_t e = 0; e < lo_len; e++) { h[e] = a; a = gl::mul(a, root); }
+        u64 b = gl::ONE;
+        for (size_t e = 0; e < hl; e++) { h[lo_len + e] = b; b = gl::mul(b, a); }
+        u64 *d = nullptr;
+        cudaError_t e = cudaMalloc(&d, h.size() * 8);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(c, MS_ERR_NOMEM, "twiddle table cudaMalloc: %s", cudaGetErrorString(e));
+        }
+        MS_CUDA(c, cudaMemcpyAsync(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        MS_CUDA(c, cudaStreamSynchronize(c->stream));
+        it = c->tw_tables.emplace(log_n, d).first;
+    }
+    *tw_lo = it->second;
+    *tw_hi = it->second + 4096;
+    *hi_len = hl;
     return MS_OK;
+}
+
+// drop every cached plan (and its big tables); plans are rebuilt on demand
+void ntt_drop_plans(ms_ctx *c) {
+    cudaStreamSynchronize(c->stream);
+    c->plans.clear();
 }
 
 __global__ void copy_strided_kernel(const u64 *src, size_t src_stride, u64 *dst, size_t dst_stride, size_t words) {
@@ -466,6 +500,7 @@ int ms_ntt_batch_to(ms_ctx *c, int field, const void *src, size_t src_stride_ele
     if (!c || !src || !dst) return MS_ERR_INVALID;
     if (src == dst && src_stride_elems == dst_stride_elems)
         return ms_ntt_batch(c, field, dst, dst_stride_elems, ncols, log_n, direction, offset_mont);
+    if (src == dst && ncols > 1) return fail(c, MS_ERR_INVALID, "ms_ntt_batch_to: src == dst with different strides");
     if (int rc = check_field(c, field)) return rc;
     if (log_n > 32 || ncols == 0) return fail(c, MS_ERR_INVALID, "ms_ntt_batch_to: bad size");
     if (offset_mont >= gl::P || offset_mont == 0) return fail(c, MS_ERR_INVALID, "offset must be a non-zero canonical word");
@@ -476,7 +511,9 @@ int ms_ntt_batch_to(ms_ctx *c, int field, const void *src, size_t src_stride_ele
     if (int rc = ntt_get_plan(c, job, &P)) return rc;
     Staged in(c, src, ((size_t)(ncols - 1) * src_stride_elems + n) * field * 8, true, false);
     if (in.rc) return in.rc;
-    Staged out(c, dst, ((size_t)(ncols - 1) * dst_stride_elems + n) * field * 8, false, true);
+    // a staged host destination is copied back as one span: with gaps between the columns (stride > n) the gaps must
+    // hold the caller's bytes, so they are copied in first
+    Staged out(c, dst, ((size_t)(ncols - 1) * dst_stride_elems + n) * field * 8, ncols > 1 && dst_stride_elems != n, true);
     if (out.rc) return out.rc;
     int rc = ntt_run(c, *P, in.as<u64>(), src_stride_elems * field, out.as<u64>(), dst_stride_elems * field, ncols);
     if (rc) return rc;
@@ -500,7 +537,7 @@ int ms_lde_batch(ms_ctx *c, int field, const void *coeffs, size_t in_stride_elem
     if (ncols > 1 && (in_stride_elems < n || out_stride_elems < N)) return fail(c, MS_ERR_INVALID, "ms_lde_batch: stride too small");
     Staged in(c, coeffs, ((size_t)(ncols - 1) * in_stride_elems + n) * field * 8, true, false);
     if (in.rc) return in.rc;
-    Staged out(c, evals, ((size_t)(ncols - 1) * out_stride_elems + N) * field * 8, false, true);
+    Staged out(c, evals, ((size_t)(ncols - 1) * out_stride_elems + N) * field * 8, ncols > 1 && out_stride_elems != N, true);
     if (out.rc) return out.rc;
     int rc;
     if (bitrev_out && log_n >= 4) {

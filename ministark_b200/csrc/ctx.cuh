@@ -39,6 +39,7 @@ struct ms_ctx {
     ms::Scratch scratch[4];            // grow-only device arenas (0: ntt tmp, 1: staging in, 2: staging out, 3: misc)
     ms::u64 *t4096[2] = {nullptr, nullptr};  // omega_4096^e forward / inverse
     std::map<std::tuple<int, unsigned, int, uint64_t, unsigned, int>, std::shared_ptr<ms::NttPlanDev>> plans;
+    std::map<unsigned, ms::u64 *> tw_tables;   // log_n -> two-level g_n^e table (4096 + n/4096 words), ntt_plan_tables
 };
 
 namespace ms {
@@ -83,6 +84,7 @@ struct NttJob {
 int ntt_get_plan(ms_ctx *c, const NttJob &job, std::shared_ptr<NttPlanDev> *out);
 // two-level table of g_n^e (forward root of unity of order 2^log_n): e = 4096*e1 + e0
 int ntt_plan_tables(ms_ctx *c, unsigned log_n, const u64 **tw_lo, const u64 **tw_hi, u32 *hi_len);
+void ntt_drop_plans(ms_ctx *c);
 // run: natural mode: in == out allowed (uses scratch 0).  LDE mode: in -> out.
 // LDE scatter (ms_lde_batch_scatter): the LAST pass writes coset block q of column 0 at block_ptr[q] (device array of
 // 2^log_blowup pointers, entries may be peer-device memory) with column stride block_col_stride, and a second copy at

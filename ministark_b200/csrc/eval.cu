@@ -28,7 +28,7 @@ namespace ms {
 
 using gl::Fq3;
 
-enum { OP_X = 0, OP_CONST, OP_TRACE, OP_NEG, OP_ADD, OP_SUB, OP_MUL, OP_INV, OP_POW, OP_STORE };
+enum { OP_X = 0, OP_CONST, OP_TRACE, OP_NEG, OP_ADD, OP_SUB, OP_MUL, OP_INV, OP_POW, OP_STORE, OP_PERIODIC };
 constexpr int kMaxRegs = 48;
 
 struct EvalParams {
@@ -107,6 +107,31 @@ __global__ void __launch_bounds__(128) eval_kernel(const EvalParams p) {
                 r[d][0] = gl::add(a0, b0);
                 break;
             }
+            case OP_SUB: {
+                const u64 a0 = r[ins.z][0], b0 = r[ins.w][0];
+                if (qa || qb) {
+                    const u64 a1 = qa ? r[ins.z][1] : 0, a2 = qa ? r[ins.z][2] : 0;
+                    const u64 b1 = qb ? r[ins.w][1] : 0, b2 = qb ? r[ins.w][2] : 0;
+                    r[d][1] = gl::sub(a1, b1);
+                    r[d][2] = gl::sub(a2, b2);
+                }
+                r[d][0] = gl::sub(a0, b0);
+                break;
+            }
+            case OP_PERIODIC: {
+                // periodic column (src/constraints.rs:107-146, src/eval_cpu.rs:234-256): a table of 2^ins.w evaluations
+                // over the coset of size interval * lde_step, repeated along the ce domain; natural order
+                const u64 pos = i & ((1ull << ins.w) - 1);
+                const u64 *col = p.col_ptr[ins.z];
+                if ((ins.x >> 8) & 1) {
+                    const u64 *c = col + pos * p.fq_words;
+                    r[d][0] = c[0];
+                    if (fq3) { r[d][1] = c[1]; r[d][2] = c[2]; }
+                } else {
+                    r[d][0] = col[pos];
+                }
+                break;
+            }
             case OP_MUL: {
                 if (!qa && !qb) {
                     r[d][0] = gl::mul(r[ins.z][0], r[ins.w][0]);
@@ -166,21 +191,36 @@ static int eval_launch(ms_ctx *c, const uint32_t *program, unsigned nprog, const
                        const std::vector<const u64 *> &cols, const std::vector<int> &col_is_q, int fq_field, unsigned log_m,
                        uint64_t offset_mont, int trace_bitrev, int out_bitrev, u64 *out_dev) {
     const size_t M = (size_t)1 << log_m;
-    // validate the program against the register file, constant pool and column table
-    for (unsigned k = 0; k < nprog; k++) {
-        const uint32_t *ins = program + 4 * k;
-        const uint32_t op = ins[0] & 0xff;
-        if (op > OP_STORE || ins[1] >= (uint32_t)kMaxRegs) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: bad instruction %u", k);
-        if (op == OP_CONST && ins[2] >= nconsts) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: constant index out of range");
-        if (op == OP_TRACE) {
-            const int is_q = (ins[0] >> 8) & 1;
-            if (ins[2] >= cols.size()) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: column %u out of range", ins[2]);
-            if (col_is_q[ins[2]] != is_q) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: column %u has the wrong field", ins[2]);
+    // validate the program against the register file, constant pool and column table; every source register must
+    // have been written by an earlier instruction
+    {
+        std::vector<char> defined(kMaxRegs, 0);
+        bool stored = false;
+        for (unsigned k = 0; k < nprog; k++) {
+            const uint32_t *ins = program + 4 * k;
+            const uint32_t op = ins[0] & 0xff;
+            if (op > OP_PERIODIC || ins[1] >= (uint32_t)kMaxRegs) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: bad instruction %u", k);
+            if (op == OP_CONST && ins[2] >= nconsts) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: constant index out of range");
+            if (op == OP_TRACE || op == OP_PERIODIC) {
+                const int is_q = (ins[0] >> 8) & 1;
+                if (ins[2] >= cols.size()) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: column %u out of range", ins[2]);
+                if (col_is_q[ins[2]] != is_q) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: column %u has the wrong field", ins[2]);
+                if (op == OP_PERIODIC && ins[3] > log_m) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: periodic table longer than the domain");
+            }
+            const bool unary = op == OP_NEG || op == OP_INV || op == OP_POW || op == OP_STORE;
+            const bool binary = op == OP_ADD || op == OP_SUB || op == OP_MUL;
+            if (unary || binary) {
+                if (ins[2] >= (uint32_t)kMaxRegs || !defined[ins[2]])
+                    return fail(c, MS_ERR_INVALID, "ms_eval_constraints: instruction %u reads register %u before it is written", k, ins[2]);
+            }
+            if (binary) {
+                if (ins[3] >= (uint32_t)kMaxRegs || !defined[ins[3]])
+                    return fail(c, MS_ERR_INVALID, "ms_eval_constraints: instruction %u reads register %u before it is written", k, ins[3]);
+            }
+            if (op == OP_STORE) stored = true;
+            else defined[ins[1]] = 1;
         }
-        if ((op == OP_NEG || op == OP_ADD || op == OP_MUL || op == OP_INV || op == OP_POW || op == OP_STORE) &&
-            ins[2] >= (uint32_t)kMaxRegs)
-            return fail(c, MS_ERR_INVALID, "ms_eval_constraints: bad register");
-        if ((op == OP_ADD || op == OP_MUL) && ins[3] >= (uint32_t)kMaxRegs) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: bad register");
+        if (!stored) return fail(c, MS_ERR_INVALID, "ms_eval_constraints: program stores no result");
     }
     // program, constants and the column pointer table are tiny: always copied to the device
     void *meta;

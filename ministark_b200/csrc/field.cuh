@@ -41,7 +41,31 @@ constexpr u64 TWO = 0x1FFFFFFFEULL;       // Montgomery form of 2 (Fq3 non-resid
 #endif
 
 // ---- canonical <-> canonical ------------------------------------------------------
-GL_HD u64 canon(u64 x) { return x >= P ? x - P : x; }
+#if defined(__CUDACC__) && (defined(MS_CANON_MAD) || defined(MS_ADD_MAD))
+// eps = 2^32 - 1 as a run-time operand: with an immediate ptxas strength-reduces  c * eps + s  back into an ALU carry chain;
+// from constant memory it stays one IMAD.WIDE on the FMA pipe
+static __constant__ u32 kEpsOperand = 0xFFFFFFFFu;
+#endif
+#if defined(__CUDA_ARCH__) && defined(MS_CANON_MAD)
+// c = carry of x + eps = (x >= p); x - p = x + c * eps (mod 2^64): the conditional subtraction as ONE multiply-add on
+// the FMA pipe instead of a 64-bit compare + subtract + select on the ALU pipe
+__device__ __forceinline__ u64 canon(u64 x) {
+    u64 r;
+    asm("{\n\t.reg .u32 x0, x1, t0, t1, c;\n\tmov.b64 {x0, x1}, %1;\n\tadd.cc.u32 t0, x0, 0xffffffff;\n\taddc.cc.u32 t1, x1, 0;\n\t"
+        "addc.u32 c, 0, 0;\n\tmad.wide.u32 %0, c, %2, %1;\n\t}"
+        : "=l"(r) : "l"(x), "r"(kEpsOperand));
+    return r;
+}
+#else
+// x >= p  <=>  high word all ones and low word non-zero; then x - p = (0 : low - 1): two compares, one decrement, one select
+GL_HD u64 canon(u64 x) {
+    u32 x0 = (u32)x, x1 = (u32)(x >> 32);
+    const bool c = (x1 == 0xFFFFFFFFu) && (x0 != 0);
+    x0 -= c ? 1u : 0u;
+    x1 = c ? 0u : x1;
+    return ((u64)x1 << 32) | x0;
+}
+#endif
 
 GL_HD u64 add(u64 a, u64 b) {  // a, b < p
     u64 s = a + b;
@@ -63,6 +87,18 @@ GL_HD u64 neg(u64 a) { return a ? P - a : 0; }
 __device__ __forceinline__ u64 pack64(u32 lo, u32 hi) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
 __device__ __forceinline__ void unpack64(u64 v, u32 &lo, u32 &hi) { asm("mov.b64 {%0,%1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
 // s = a + t; on carry add eps = 2^32 - 1, i.e. low -= c, high += c - borrow
+#if defined(MS_ADD_MAD)
+// the repair s += c * eps as a multiply-add (FMA pipe): 3 ALU + 1 IMAD.WIDE instead of 6 ALU instructions
+__device__ __forceinline__ u64 add_lc(u64 a, u64 t) {
+    u32 a0, a1, t0, t1;
+    u64 r;
+    unpack64(a, a0, a1); unpack64(t, t0, t1);
+    asm("{\n\t.reg .u32 s0, s1, c;\n\t.reg .u64 s;\n\tadd.cc.u32 s0, %1, %3;\n\taddc.cc.u32 s1, %2, %4;\n\taddc.u32 c, 0, 0;\n\t"
+        "mov.b64 s, {s0, s1};\n\tmad.wide.u32 %0, c, %5, s;\n\t}"
+        : "=l"(r) : "r"(a0), "r"(a1), "r"(t0), "r"(t1), "r"(kEpsOperand));
+    return r;
+}
+#else
 __device__ __forceinline__ u64 add_lc(u64 a, u64 t) {
     u32 a0, a1, t0, t1, s0, s1;
     unpack64(a, a0, a1); unpack64(t, t0, t1);
@@ -71,6 +107,7 @@ __device__ __forceinline__ u64 add_lc(u64 a, u64 t) {
         : "=r"(s0), "=r"(s1) : "r"(a0), "r"(a1), "r"(t0), "r"(t1));
     return pack64(s0, s1);
 }
+#endif
 // d = a - t; on borrow subtract eps (m = 0xffffffff is eps as a low word)
 __device__ __forceinline__ u64 sub_lc(u64 a, u64 t) {
     u32 a0, a1, t0, t1, s0, s1;

@@ -11,6 +11,8 @@
 // consecutive threads take consecutive rows), each word is taken out of Montgomery form with
 // one reduction, byte-swapped into the big-endian SHA message schedule and compressed.  This
 // kernel is INT32-ALU bound (about 2k instructions per 64-byte block), not HBM bound.
+#include <mutex>
+#include <cstring>
 #include "ctx.cuh"
 #include <algorithm>
 #include <cstring>
@@ -43,8 +45,12 @@ __device__ __forceinline__ u32 small_sigma1(u32 w) { return rotr(w, 17) ^ rotr(w
 // K[i] + W[i] of the constant second block of a 64-byte message (0x80, zeros, bit length 512): the
 // Merkle node hash needs no message schedule for it.
 __constant__ u32 c_KW_pad64[64];
-// same for the padding block that follows a leaf row whose length is a multiple of 64 bytes (set per launch)
-__constant__ u32 c_KW_padrow[64];
+// same for the padding block that follows a leaf row whose length is a multiple of 64 bytes: per-LAUNCH state, passed
+// as a __grid_constant__ kernel argument (constant bank, compile-time indices) — a __constant__ symbol would be shared by
+// every context and stream of the device and could be re-uploaded under a kernel still in flight
+struct KW64 {
+    u32 v[64];
+};
 
 // Pipe balancing: SHF/LOP3/IADD3 all issue on the 64-lane ALU pipe while the FMA pipe idles.  fma_add() forces
 // an addition onto the FMA pipe as IMAD (x * c_one + y); c_one lives in constant memory so ptxas cannot fold it
@@ -131,7 +137,8 @@ using Sha = ShaT<0>;
 template <int V>
 __global__ void __launch_bounds__(128) hash_rows_kernel(const u64 *__restrict__ cols, size_t col_stride_words,
                                                          unsigned lanes, unsigned words_per_row, size_t nrows,
-                                                         u32 *__restrict__ digests, int const_pad) {
+                                                         u32 *__restrict__ digests, int const_pad,
+                                                         const __grid_constant__ KW64 kw_pad) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= nrows) return;
     ShaT<V> s;
@@ -163,7 +170,7 @@ __global__ void __launch_bounds__(128) hash_rows_kernel(const u64 *__restrict__ 
         }
         s.compress(w);
     }
-    if (const_pad) s.compress_const(c_KW_padrow);
+    if (const_pad) s.compress_const(kw_pad.v);
     s.store(digests + i * 8);
 }
 
@@ -232,14 +239,15 @@ static int sha_variant() {
     if (sha_variant() == 0) KERNEL<0><<<GRID, 128, 0, c->stream>>>(__VA_ARGS__);   \
     else KERNEL<7><<<GRID, 128, 0, c->stream>>>(__VA_ARGS__);
 
-static int upload_row_pad_schedule(ms_ctx *c, unsigned row_words);
+static int row_pad_schedule(unsigned row_words, KW64 *kw);
 static int hash_rows_dev(ms_ctx *c, int field, const u64 *cols, size_t col_stride_elems, unsigned ncols, size_t nrows,
                          u32 *digests) {
     if (nrows == 0) return MS_OK;
     const unsigned threads = 128;
-    const int const_pad = upload_row_pad_schedule(c, ncols * field);
+    KW64 kw;
+    const int const_pad = row_pad_schedule(ncols * field, &kw);
     MS_SHA_DISPATCH(hash_rows_kernel, (unsigned)((nrows + threads - 1) / threads), cols, col_stride_elems * field, (unsigned)field,
-                    ncols * field, nrows, digests, const_pad);
+                    ncols * field, nrows, digests, const_pad, kw);
     c->launches++;
     MS_CHECK_LAUNCH(c);
     return MS_OK;
@@ -250,6 +258,8 @@ static u32 h_rotr(u32 x, int r) { return (x >> r) | (x << (32 - r)); }
 static void pad_schedule(unsigned long long bitlen, u32 kw[64]);
 static int upload_pad_schedule(ms_ctx *c) {
     static bool done[64] = {false};
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);   // the constant is the same for every context: upload once per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && done[dev]) return MS_OK;
@@ -259,23 +269,11 @@ static int upload_pad_schedule(ms_ctx *c) {
     if (dev >= 0 && dev < 64) done[dev] = true;
     return MS_OK;
 }
-// leaf rows: returns 1 (and uploads the schedule) if row_words*8 bytes is a multiple of 64, else 0
-static int upload_row_pad_schedule(ms_ctx *c, unsigned row_words) {
+// leaf rows: returns 1 (and fills the schedule) if row_words*8 bytes is a multiple of 64, else 0
+static int row_pad_schedule(unsigned row_words, KW64 *kw) {
+    memset(kw, 0, sizeof *kw);
     if (row_words % 8) return 0;
-    static unsigned long long last[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const unsigned long long bitlen = (unsigned long long)row_words * 64;
-    if (dev >= 0 && dev < 64 && last[dev] == bitlen) return 1;
-    u32 kw[64];
-    pad_schedule(bitlen, kw);
-    // stream-ordered so that a launch still in flight with another row length is not disturbed
-    if (cudaMemcpyToSymbolAsync(c_KW_padrow, kw, sizeof kw, 0, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
-    cudaStreamSynchronize(c->stream);   // kw is a stack buffer
-    if (dev >= 0 && dev < 64) last[dev] = bitlen;
+    pad_schedule((unsigned long long)row_words * 64, kw->v);
     return 1;
 }
 static void pad_schedule(unsigned long long bitlen, u32 kw[64]) {
@@ -403,9 +401,10 @@ int ms_merkle_commit_rows_sha256(ms_ctx *c, const void *rows, unsigned row_words
     else if ((rc = scratch_get(c, 3, nrows * 32, &nd))) return rc;
     // one "column" whose element is the whole row: word t of row i at base + i*row_words + t
     const unsigned threads = 128;
-    const int const_pad = upload_row_pad_schedule(c, row_words);
+    KW64 kw;
+    const int const_pad = row_pad_schedule(row_words, &kw);
     MS_SHA_DISPATCH(hash_rows_kernel, (unsigned)((nrows + threads - 1) / threads), in.as<u64>(), (size_t)0, row_words, row_words, nrows,
-                    (u32 *)lv, const_pad);
+                    (u32 *)lv, const_pad, kw);
     c->launches++;
     MS_CHECK_LAUNCH(c);
     if ((rc = merkle_nodes_dev(c, (const u32 *)lv, nrows, (u32 *)nd))) return rc;

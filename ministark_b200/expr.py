@@ -3,8 +3,8 @@
 Host-side mirror of the reference's input format for constraint evaluation:
     Expr<AlgebraicItem<FieldVariant<Fp, Fq>>>        src/expression.rs:31-39, src/constraints.rs:21-28
 with leaves  X | Constant | Challenge(i) | Hint(i) | Trace(column, row offset)  and nodes
-Neg | Add | Mul | Div | Pow(usize).  (Periodic columns are not supported yet; neither BASELINE
-AIR uses them.)
+Neg | Add | Mul | Div | Pow(usize), and  Periodic(coeffs, interval_size)  (src/constraints.rs:107-146): the polynomial
+with these coefficients in  y = x^(trace_len / interval_size), i.e. a column that repeats every interval_size rows.
 
 The reference evaluates this DAG either with one GPU dispatch + barrier + full HBM round trip per
 node (eval_gpu.rs, disabled: src/air.rs:104-117) or on the CPU in 512-element chunks
@@ -22,7 +22,7 @@ _RINV = pow(_R, -1, P)
 FP, FQ = 0, 1  # value types: base field / extension ("Fq" is Fq3, or Fp itself when the AIR has Fq = Fp)
 
 # opcodes (must match csrc/eval.cu)
-OP_X, OP_CONST, OP_TRACE, OP_NEG, OP_ADD, OP_SUB, OP_MUL, OP_INV, OP_POW, OP_STORE = range(10)
+OP_X, OP_CONST, OP_TRACE, OP_NEG, OP_ADD, OP_SUB, OP_MUL, OP_INV, OP_POW, OP_STORE, OP_PERIODIC = range(11)
 MAX_REGS = 48
 
 
@@ -138,12 +138,25 @@ def Trace(col, offset=0):
     return Expr("trace", int(col), int(offset))
 
 
+def Periodic(coeffs, interval_size):
+    """PeriodicColumn::new (src/constraints.rs:107-126): coefficients (canonical ints, or 3-tuples for extension
+    elements) of a polynomial in x^(trace_len / interval_size); both lengths are powers of two, len(coeffs) <= interval"""
+    coeffs = tuple(tuple(int(x) % P for x in c) if isinstance(c, (tuple, list)) else int(c) % P for c in coeffs)
+    n, m = len(coeffs), int(interval_size)
+    if n == 0 or n & (n - 1) or m & (m - 1) or n > m:
+        raise ValueError("periodic column: lengths must be powers of two with len(coeffs) <= interval_size")
+    return Expr("periodic", coeffs, m)
+
+
 class Program:
-    def __init__(self, code, consts, nregs, out_is_q, bindings=()):
+    def __init__(self, code, consts, nregs, out_is_q, bindings=(), periodic=()):
         self.code = np.ascontiguousarray(code, dtype=np.uint32).reshape(-1, 4)
         self.consts = np.ascontiguousarray(consts, dtype=np.uint64).reshape(-1, 3)
         self.nregs, self.out_is_q = nregs, out_is_q
         self.bindings = list(bindings)          # (constant slot, "chal" | "hint" | "ccoef", index): filled by bind()
+        # periodic columns: (column slot in the evaluator's column table, coeffs, interval_size, is_ext, log2 of the
+        # table length = interval_size * lde_step); the tables are built by periodic_tables() and appended to the columns
+        self.periodic = list(periodic)
 
     def bind(self, challenges=(), hints=(), ccoefs=()):
         """a copy of this program whose symbolic constants hold this proof's verifier randomness.  The instruction
@@ -153,7 +166,7 @@ class Program:
         consts = self.consts.copy()
         for slot, kind, idx in self.bindings:
             consts[slot] = [c * _R % P for c in _q(src[kind][idx])]
-        return Program(self.code, consts, self.nregs, self.out_is_q)
+        return Program(self.code, consts, self.nregs, self.out_is_q, periodic=self.periodic)
 
     def __len__(self):
         return self.code.shape[0]
@@ -162,8 +175,37 @@ class Program:
 _SYMBOLIC = ("chal", "hint", "ccoef")
 
 
-def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, log_ce=None, fold_pow0=True, symbolic=False):
+def periodic_tables(ctx, program, log_n, lde_step, offset_canonical=7):
+    """eval_periodic_column (src/eval_cpu.rs:234-256) for every periodic column of `program`, on the device: the
+    coefficients zero-padded to interval_size * lde_step, transformed over the coset  offset^(n / interval) * <g>  —
+    natural order; the evaluator indexes the table with (point index mod table length).  Returns a list of
+    (device pointer, is_ext); the caller appends them to the column list in program.periodic order and keeps the
+    pointers alive until the evaluation has run (ctx.free them afterwards)."""
+    import ctypes as C
+    out = []
+    n = 1 << log_n
+    for _, coeffs, interval, is_q, log_len in program.periodic:
+        lanes = 3 if is_q else 1
+        length = 1 << log_len
+        host = np.zeros(length * lanes, dtype=np.uint64)
+        for k, c in enumerate(coeffs):
+            v = c if isinstance(c, tuple) else (c, 0, 0)
+            for w in range(lanes):
+                host[k * lanes + w] = v[w] * _R % P
+        off = pow(offset_canonical, n // interval, P) * _R % P
+        ctx.ntt_batch(host, lanes, log_len, 1, offset=off)          # host buffer: staged through the device
+        ptr = ctx.alloc_device(host.nbytes)
+        ctx._ck(ctx.lib.ms_copy(ctx.h, ptr, host.ctypes.data, host.nbytes))
+        out.append((ptr, is_q))
+    return out
+
+
+def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, log_ce=None, fold_pow0=True, symbolic=False,
+                    num_cols=None):
     """Flatten `expr` into the evaluator's linear program.
+
+    num_cols: total number of trace columns (base + extension); periodic tables take the column slots after them
+    (required when the expression has Periodic leaves).
 
     symbolic=True keeps Challenge / Hint / CompositionCoeff leaves as run-time constants (Program.bind fills them in)
     instead of folding their values into the program: compile once per AIR, bind per proof.
@@ -249,6 +291,8 @@ def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, lo
             typ[id(nd)] = FP
         elif k == "trace":
             typ[id(nd)] = FP if a[0] < num_base_cols else FQ
+        elif k == "periodic":
+            typ[id(nd)] = FQ if any(isinstance(c, tuple) for c in a[0]) else FP
         else:
             kids = [x for x in a if isinstance(x, Expr)]
             typ[id(nd)] = max(typ[id(x)] for x in kids)
@@ -286,9 +330,10 @@ def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, lo
     leaf_regs, pinned, touch = {}, set(), {}
 
     bindings, sym_slot = [], {}
+    periodic, periodic_slot = [], {}
 
     def is_leaf(x):
-        return id(x) in cval or x.kind in ("x", "trace") or x.kind in _SYMBOLIC
+        return id(x) in cval or x.kind in ("x", "trace", "periodic") or x.kind in _SYMBOLIC
 
     def alloc():
         nonlocal nregs
@@ -317,6 +362,18 @@ def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, lo
             code.append([OP_CONST | (FQ << 8), r, sym_slot[key], 0])
         elif x.kind == "x":
             code.append([OP_X, r, 0, 0])
+        elif x.kind == "periodic":
+            coeffs, interval = x.args
+            if num_cols is None:
+                raise ValueError("compile_program: num_cols is needed to place the periodic tables")
+            if id(x) not in periodic_slot:
+                log_len = (interval * lde_step).bit_length() - 1
+                if log_ce is not None and log_len > log_ce:
+                    raise ValueError("periodic column interval exceeds the trace length")
+                periodic_slot[id(x)] = num_cols + len(periodic)
+                periodic.append((periodic_slot[id(x)], coeffs, interval, typ[id(x)] == FQ, log_len))
+            slot = periodic_slot[id(x)]
+            code.append([OP_PERIODIC | (typ[id(x)] << 8), r, slot, periodic[slot - num_cols][4]])
         else:
             col, off = x.args
             shift = lde_step * off
@@ -375,4 +432,4 @@ def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, lo
         reg_of[id(nd)] = r
     code.append([OP_STORE | (typ[id(expr)] << 8), 0, reg_of[id(expr)], 0])
     return Program(np.array(code, dtype=np.uint32), np.array(consts if consts else [[0, 0, 0]], dtype=np.uint64),
-                   max(nregs, 1), typ[id(expr)] == FQ, bindings)
+                   max(nregs, 1), typ[id(expr)] == FQ, bindings, periodic)

@@ -6,6 +6,7 @@ Restates AirConfig::eval_constraint -> eval_cpu::eval (src/air.rs:86-128, src/ev
 
 Expression exchange format: nested tuples
     ('x',) | ('const', (c0,c1,c2), is_ext) | ('chal', i) | ('hint', i) | ('trace', col, row_offset)
+    ('periodic', coeffs, interval_size)            src/constraints.rs:107-146, src/eval_cpu.rs:176-256
     ('neg', a) | ('add', a, b) | ('mul', a, b) | ('div', a, b) | ('pow', a, e)
 Columns: natural-order evaluations over the ce coset (what bit_reverse_ce_trace hands to
 eval_constraint, src/prover.rs:86-91).
@@ -80,6 +81,25 @@ def evaluate(expr, log_m, offset_mont, base_cols, ext_cols=None, fq_lanes=1, cha
             else:
                 src, lanes = ext_cols[col - nbase], fq_lanes
             r = (np.roll(src.reshape(m, lanes), -shift, axis=0).reshape(-1).copy(), lanes, False)
+        elif k == 'periodic':
+            # eval_periodic_column (src/eval_cpu.rs:234-256) by the definition: P(y) at y = (offset * g_m^i)^(n / interval),
+            # one evaluation per point of the domain of size interval * lde_step, repeated along the ce domain
+            coeffs, interval = e[1], e[2]
+            n = m // lde_step
+            lanes = fq_lanes if any(isinstance(c, tuple) for c in coeffs) else 1
+            period = interval * lde_step
+            off = S.from_mont(int(offset_mont))
+            g = S.root_of_unity(log_m)
+            table = []
+            for i in range(period):
+                y = pow(off * pow(g, i, S.P) % S.P, n // interval, S.P)
+                cs = [c if isinstance(c, tuple) else (c, 0, 0) for c in coeffs]
+                acc = [0, 0, 0]
+                for c in reversed(cs):
+                    acc = [(acc[w] * y + c[w]) % S.P for w in range(3)]
+                table.append([S.to_mont(acc[w]) for w in range(lanes)])
+            tab = np.array(table, dtype=np.uint64).reshape(period, lanes)
+            r = (np.tile(tab, (m // period, 1)).reshape(-1).copy(), lanes, False)
         elif k == 'neg':
             a = walk(e[1])
             r = (orc.pointwise("neg", as_array(a), a[1]), a[1], False)

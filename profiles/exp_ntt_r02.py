@@ -142,10 +142,26 @@ def bench():
         emit(bench="intt_32x2p24", variant=name, ms_min=round(mn, 3), ms_med=round(med, 3))
 
 
+def prof():
+    """one small LDE (4 columns x 2^24, x8) for ncu: run under `ncu -k regex:ntt_tma -s 3 -c 3 --set full`"""
+    ctx = new_ctx()
+    log_n, log_b, ncols = 24, 3, 4
+    n = 1 << log_n
+    tr = torch.empty((ncols, n), dtype=torch.int64, device="cuda")
+    ctx.fill_random(tr, ncols * n, 3)
+    lde = torch.empty((ncols, n << log_b), dtype=torch.int64, device="cuda")
+    for _ in range(2):
+        ctx.lde_batch(tr, lde, ms.FP, log_n, log_b, ncols)
+    ctx.sync()
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "check"
     t0 = time.time()
     if what == "check":
         sys.exit(0 if check() else 1)
-    bench()
+    if what == "prof":
+        prof()
+    else:
+        bench()
     print("elapsed", time.time() - t0)

@@ -28,34 +28,49 @@ from oracle import oracle as orc  # noqa: E402
 from oracle import synth_oracle  # noqa: E402
 
 P = 2**64 - 2**32 + 1
-M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
 
 
-def device_fill_random(nwords, seed):
-    """ms_fill_random (csrc/api_core.cu fill_random_kernel) restated: word i = Montgomery form of the first splitmix64
-    draw < p of the stream seeded with seed ^ (0xD1B54A32D192ED03 * (i + 1))."""
+def device_fill_random_range(i0, count, seed):
+    """ms_fill_random (csrc/api_core.cu fill_random_kernel) restated, words [i0, i0 + count): word i = Montgomery form of
+    the first splitmix64 draw < p of the stream seeded with seed ^ (0xD1B54A32D192ED03 * (i + 1))."""
     with np.errstate(over="ignore"):
-        i = np.arange(1, nwords + 1, dtype=np.uint64)
+        i = np.arange(i0 + 1, i0 + count + 1, dtype=np.uint64)
         s = np.uint64(seed) ^ (np.uint64(0xD1B54A32D192ED03) * i)
-        out = np.empty(nwords, dtype=np.uint64)
-        todo = np.arange(nwords)
-        while todo.size:
-            s_t = s[todo] + np.uint64(0x9E3779B97F4A7C15)
-            s[todo] = s_t
-            z = s_t
-            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-            z = z ^ (z >> np.uint64(31))
+        del i
+        out = np.empty(count, dtype=np.uint64)
+        todo = None
+        while True:
+            cur = s if todo is None else s[todo]
+            cur = cur + np.uint64(0x9E3779B97F4A7C15)
+            z = cur.copy()
+            z ^= z >> np.uint64(30)
+            z *= np.uint64(0xBF58476D1CE4E5B9)
+            z ^= z >> np.uint64(27)
+            z *= np.uint64(0x94D049BB133111EB)
+            z ^= z >> np.uint64(31)
             good = z < np.uint64(P)
-            out[todo[good]] = z[good]
-            todo = todo[~good]
+            if todo is None:
+                s = cur
+                out[:] = z
+                bad = np.nonzero(~good)[0]
+            else:
+                s[todo] = cur
+                out[todo[good]] = z[good]
+                bad = todo[~good]
+            if bad.size == 0:
+                break
+            todo = bad
     return orc.to_mont(out)
 
 
 def trace_blocks(log_n, ncols_per, world, seed=3000):
-    """(world * ncols_per, n): rank r's block is ms_fill_random(ncols_per * n words, seed + r)"""
+    """(world * ncols_per, n): rank r's block is ms_fill_random(ncols_per * n words, seed + r); built column by column"""
     n = 1 << log_n
-    return np.concatenate([device_fill_random(ncols_per * n, seed + r).reshape(ncols_per, n) for r in range(world)])
+    out = np.empty((world * ncols_per, n), dtype=np.uint64)
+    for r in range(world):
+        for c in range(ncols_per):
+            out[r * ncols_per + c] = device_fill_random_range(c * n, n, seed + r)
+    return out
 
 
 def brev(v, bits):
@@ -78,14 +93,26 @@ def streamed_commit(polys, log_n, log_b):
         if q == 0:
             block0 = ev
     nodes = orc.merkle_nodes(leaves)
-    return nodes[1].tobytes(), block0
+    root = nodes[1].tobytes()
+    del nodes, leaves
+    return root, block0
 
 
 def case(log_n, ncols_per, world, log_b=3, check_streaming=False):
     t0 = time.time()
     trace = trace_blocks(log_n, ncols_per, world)
+    trace_sha = hashlib.sha256(trace.tobytes() if log_n <= 20 else memoryview(trace.reshape(-1))).hexdigest()
     polys = orc.ntt(trace, 1, log_n, inverse=True)
+    del trace
+    polys0_sha = hashlib.sha256(polys[0].tobytes()).hexdigest()
     root, block0 = streamed_commit(polys, log_n, log_b)
+    if check_streaming:
+        lde = orc.lde(polys, 1, log_n, log_b, orc.generator(), bitrev=True)
+        want = orc.merkle_nodes(orc.hash_rows(lde, 1))[1].tobytes()
+        assert want == root, "streamed commitment differs from the direct oracle path"
+        assert np.array_equal(lde[:, :1 << log_n], block0)
+        del lde
+    del polys
     # composition: every rank evaluates the 32-column AIR on its own block; the partial columns are summed
     total = None
     for r in range(world):
@@ -94,18 +121,13 @@ def case(log_n, ncols_per, world, log_b=3, check_streaming=False):
         total = ce if total is None else orc.pointwise("add", total, 1, ce, 1)
     out = {
         "log_n": log_n, "ncols_per_rank": ncols_per, "world": world, "log_blowup": log_b, "seed": 3000,
-        "trace_sha256": hashlib.sha256(trace.tobytes()).hexdigest(),
-        "polys_col0_sha256": hashlib.sha256(polys[0].tobytes()).hexdigest(),
+        "trace_sha256": trace_sha,
+        "polys_col0_sha256": polys0_sha,
         "lde_block0_col0_sha256": hashlib.sha256(block0[0].tobytes()).hexdigest(),
         "merkle_root": root.hex(),
         "constraint_eval_sha256": hashlib.sha256(np.ascontiguousarray(total).tobytes()).hexdigest(),
         "constraint_eval_first": [int(x) for x in np.ascontiguousarray(total).reshape(-1)[:4]],
     }
-    if check_streaming:
-        lde = orc.lde(polys, 1, log_n, log_b, orc.generator(), bitrev=True)
-        want = orc.merkle_nodes(orc.hash_rows(lde, 1))[1].tobytes()
-        assert want == root, "streamed commitment differs from the direct oracle path"
-        assert np.array_equal(lde[:, :1 << log_n], block0)
     print(f"case 2^{log_n} x {ncols_per}*{world}: {time.time() - t0:.1f} s, root {root.hex()[:16]}", flush=True)
     return out
 

@@ -110,3 +110,41 @@ def test_deep_program_symbolic_equals_plain(which):
     for row in (0, 7, m - 1):
         x = rng.randrange(2, P)
         assert run_program(bound, x, cols, is_q, row, m) == run_program(plain, x, cols, is_q, row, m)
+
+
+def test_periodic_columns_compile_and_degree():
+    """Periodic(coeffs, interval) (src/constraints.rs:107-146): the compiled program reads a table of interval * lde_step
+    evaluations (eval_periodic_column, src/eval_cpu.rs:234-256) that repeats along the ce domain; the value must equal the
+    verifier's P(x^(n / interval)) (src/verifier.rs:221-230) at every point x = offset * g^row"""
+    from ministark_b200 import air as A
+    from tests_helpers_expr import periodic_value
+    rng = random.Random(3)
+    n, lde_step = 8, 2
+    m = n * lde_step
+    log_m = m.bit_length() - 1
+    g = A.domain_generator(log_m)
+    pa = E.Periodic([3, 5], 4)                                                  # base-field coefficients
+    pb = E.Periodic([(1, 2, 3), (4, 5, 6), (7, 8, 9), (10, 11, 12)], 8)         # extension coefficients
+    cols, is_q = random_columns(rng, 2, 1, m)
+    expr = (E.Trace(0, 1) - pa * E.Trace(1, 0)) * pb + E.Trace(2, 0) * pa * pa - E.X()
+    prog = E.compile_program(expr, 2, lde_step=lde_step, log_ce=log_m, num_cols=3)
+    assert [(slot, interval, q, ll) for slot, _, interval, q, ll in prog.periodic] == [(3, 4, False, 3), (4, 8, True, 4)] or \
+        [(slot, interval, q, ll) for slot, _, interval, q, ll in prog.periodic] == [(3, 8, True, 4), (4, 4, False, 3)]
+    xs = [A.GENERATOR * pow(g, i, P) % P for i in range(m)]
+    tables, tq = [], []
+    for _, coeffs, interval, q, log_len in prog.periodic:
+        vals = [periodic_value(coeffs, interval, xs[i], n) for i in range(1 << log_len)]
+        tables.append([v if q else v[0] for v in vals])
+        tq.append(q)
+        # the table really is periodic along the domain
+        assert all(periodic_value(coeffs, interval, xs[i], n) == vals[i % (1 << log_len)] for i in range(m))
+    for row in range(m):
+        want = direct(expr, xs[row], cols, row, m, lde_step=lde_step)
+        assert run_program(prog, xs[row], cols + tables, is_q + tq, row, m) == want
+    # degree rule: (len(coeffs) - 1) * (trace_len / interval)
+    assert A.degree(pa, n - 1) == (1 * (n // 4), 0)
+    assert A.degree(pb * E.Trace(0, 0), n - 1) == (3 * (n // 8) + n - 1, 0)
+    with pytest.raises(ValueError):
+        E.Periodic([1, 2, 3], 4)
+    with pytest.raises(ValueError):
+        E.compile_program(pa, 2, lde_step=lde_step, log_ce=log_m)              # num_cols missing

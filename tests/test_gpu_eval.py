@@ -93,3 +93,74 @@ def test_program_validation(ctx):
     base = np.zeros((2, 16), dtype=np.uint64)
     with pytest.raises(ms.MsError):          # column 5 referenced, only 2 provided (panics in eval_cpu.rs:148)
         ctx.eval_constraints(prog, out, 4, base_cols=base, nbase=2)
+
+
+@pytest.mark.parametrize("bitrev", [False, True])
+@pytest.mark.parametrize("blowup", [1, 4])
+def test_periodic_columns(ctx, orc, bitrev, blowup):
+    """Periodic(coeffs, interval) leaves (src/constraints.rs:107-146, src/eval_cpu.rs:176-256): tables built on the device
+    (expr.periodic_tables), evaluator (interpreter and run-time specialised kernel) vs the oracle's definition"""
+    torch = pytest.importorskip("torch")
+    from oracle import eval_oracle
+    log_n = 9
+    log_m = log_n + (blowup.bit_length() - 1)
+    m = 1 << log_m
+    base = orc.rand_matrix(2, m, 1, seed=21)
+    ext = orc.rand_matrix(1, m, 3, seed=22)
+    pa = E.Periodic([3, 5, 11, 2], 8)
+    pb = E.Periodic([(1, 2, 3), (4, 5, 6)], 64)
+    ex = (E.Trace(0, 1) - pa * E.Trace(1, 0)) * pb + E.Trace(2, 0) * pa * pa - E.X() * pb
+    prog = E.compile_program(ex, 2, lde_step=blowup, log_ce=log_m, num_cols=3)
+    cols_np = [base[0], base[1], ext[0]]
+    if bitrev:
+        cols_np = [orc.bit_reverse(base[0], 1, log_m), orc.bit_reverse(base[1], 1, log_m), orc.bit_reverse(ext[0], 3, log_m)]
+    dev = [torch.from_numpy(c.view(np.int64).copy()).cuda() for c in cols_np]
+    tabs = E.periodic_tables(ctx, prog, log_n, blowup)
+    out = torch.empty(m * 3, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    want = eval_oracle.evaluate(ex.to_tuple(), log_m, orc.generator(), base, ext, fq_lanes=3, lde_step=blowup)
+    import os
+    for no_jit in (False, True):
+        if no_jit:
+            os.environ["MS_EVAL_NO_JIT"] = "1"
+        try:
+            out.zero_()
+            torch.cuda.synchronize()
+            ctx.eval_constraints_ptrs(prog, out, log_m, dev + [p for p, _ in tabs], [False, False, True] + [q for _, q in tabs],
+                                      fq_field=3, trace_bitrev=bitrev)
+            ctx.sync()
+        finally:
+            os.environ.pop("MS_EVAL_NO_JIT", None)
+        assert np.array_equal(out.cpu().numpy().view(np.uint64), want)
+    for p, _ in tabs:
+        ctx.free(p)
+
+
+def test_sub_opcode_and_register_validation(ctx):
+    """OP_SUB (declared in the instruction set, emitted by the C++ host compiler) in both evaluators, and the
+    defined-before-use check of source registers"""
+    torch = pytest.importorskip("torch")
+    import os
+    log_m = 6
+    m = 1 << log_m
+    c5 = 5 * 2**64 % P
+    consts = np.array([[c5, 0, 0]], dtype=np.uint64)
+    code = np.array([[E.OP_X, 0, 0, 0], [E.OP_CONST, 1, 0, 0], [E.OP_SUB, 2, 1, 0], [E.OP_STORE, 0, 2, 0]], dtype=np.uint32)
+    prog = E.Program(code, consts, 3, False)
+    g = pow(pow(7, (P - 1) >> 32, P), 1 << (32 - log_m), P)
+    want = np.array([((5 - 7 * pow(g, i, P)) % P) * 2**64 % P for i in range(m)], dtype=np.uint64)
+    out = torch.empty(m, dtype=torch.int64, device="cuda")
+    for no_jit in (False, True):
+        if no_jit:
+            os.environ["MS_EVAL_NO_JIT"] = "1"
+        try:
+            out.zero_()
+            torch.cuda.synchronize()
+            ctx.eval_constraints_ptrs(prog, out, log_m, [], [], fq_field=1)
+            ctx.sync()
+        finally:
+            os.environ.pop("MS_EVAL_NO_JIT", None)
+        assert np.array_equal(out.cpu().numpy().view(np.uint64), want)
+    bad = E.Program(np.array([[E.OP_X, 0, 0, 0], [E.OP_ADD, 2, 0, 7], [E.OP_STORE, 0, 2, 0]], dtype=np.uint32), consts, 3, False)
+    with pytest.raises(ms.MsError):          # register 7 is read but never written
+        ctx.eval_constraints_ptrs(bad, out, log_m, [], [], fq_field=1)

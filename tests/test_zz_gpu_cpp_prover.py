@@ -2,9 +2,8 @@
 C ABI and must emit exactly the bytes of the Python driver (ministark_b200/prover.py) for the same trace — which are
 in turn byte-identical to the CPU restatement of the reference prover (tests/test_gpu_stark.py).
 
-The C++ host logic is CPU-tested (tests/test_cpp_host.py); the GPU-calling driver was written after this round's GPU
-budget was spent, so its first run on a device is the driver's round-end test run: non-strict xfail until it has been
-seen to pass once (the file name makes it run last)."""
+The C++ host logic is CPU-tested (tests/test_cpp_host.py); these device runs passed on the B200 at the end of round 1
+(GPUTEST_r01: 4 xpassed) and are ordinary tests since."""
 import os
 import subprocess
 
@@ -27,7 +26,6 @@ def _build(tmp_path):
     return exe
 
 
-@pytest.mark.xfail(reason="first device run of the C++ driver (written after the round's GPU budget was used up)", strict=False)
 @pytest.mark.parametrize("log_rows,opts", [(7, (16, 4, 4, 8, 16)), (12, (32, 4, 8, 8, 64))])
 def test_cpp_prover_bytes_equal_python_prover(tmp_path, log_rows, opts):
     exe = _build(tmp_path)
@@ -40,7 +38,6 @@ def test_cpp_prover_bytes_equal_python_prover(tmp_path, log_rows, opts):
     assert bytes.fromhex(hexbytes) == want
 
 
-@pytest.mark.xfail(reason="first device run of the C++ driver (written after the round's GPU budget was used up)", strict=False)
 @pytest.mark.parametrize("which,opts", [("hello", (19, 16, 20, 16, 16)), ("burner:4:4:4", (16, 16, 6, 8, 8))])
 def test_cpp_prover_brainfuck_bytes_equal_python_prover(tmp_path, which, opts):
     """extension columns built on the device by the C++ twin of _device_extension (evaluator + ms_scan_affine)"""

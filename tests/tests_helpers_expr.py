@@ -27,6 +27,11 @@ def run_program(prog, x, cols, col_is_q, row, m):
             regs[d] = E.q_neg(regs[a])
         elif op == E.OP_ADD:
             regs[d] = E.q_add(regs[a], regs[b])
+        elif op == E.OP_SUB:
+            regs[d] = E.q_add(regs[a], E.q_neg(regs[b]))
+        elif op == E.OP_PERIODIC:
+            v = cols[a][row % (1 << b)]          # the table rides in the column list after the trace columns
+            regs[d] = tuple(v) if qa else (v, 0, 0)
         elif op == E.OP_MUL:
             regs[d] = E.q_mul(regs[a], regs[b])
         elif op == E.OP_INV:
@@ -39,6 +44,16 @@ def run_program(prog, x, cols, col_is_q, row, m):
             raise AssertionError(op)
         assert d < E.MAX_REGS
     return out
+
+
+def periodic_value(coeffs, interval, x, n):
+    """P(x^(n / interval)) by Horner, the verifier's formula (src/verifier.rs:221-230)"""
+    y = pow(x, n // interval, P)
+    acc = (0, 0, 0)
+    for c in reversed(coeffs):
+        c = c if isinstance(c, tuple) else (c, 0, 0)
+        acc = E.q_add(E.q_mul(acc, (y, 0, 0)), c)
+    return acc
 
 
 def direct(expr, x, cols, row, m, challenges=(), hints=(), ccoefs=(), lde_step=1):
@@ -61,6 +76,8 @@ def direct(expr, x, cols, row, m, challenges=(), hints=(), ccoefs=(), lde_step=1
         elif k == "trace":
             t = cols[a[0]][(row + lde_step * a[1]) % m]
             v = tuple(t) if isinstance(t, tuple) else (t, 0, 0)
+        elif k == "periodic":
+            v = periodic_value(a[0], a[1], x, m // lde_step)
         elif k == "neg":
             v = E.q_neg(ev(a[0]))
         elif k == "add":
