@@ -113,6 +113,29 @@ def ncu_traffic():
     return None
 
 
+def golden_entry(log_n, ncols, world):
+    """committed oracle outputs for this workload (tests/golden/config3.json, made by tests/golden/make_config3_golden.py):
+    the bench never runs the oracle for this — it compares against the fixture"""
+    p = os.path.join(ROOT, "tests", "golden", "config3.json")
+    try:
+        return json.load(open(p)).get(f"2^{log_n}x{ncols}x{world}")
+    except Exception:
+        return None
+
+
+def check_against_golden(g, root, ce_tensor, what):
+    import hashlib
+    if g is None:
+        return {"golden": None, "note": f"no committed fixture for {what}"}
+    got_root = root.hex()
+    ce_sha = hashlib.sha256(ce_tensor.cpu().numpy().tobytes()).hexdigest()
+    ok_root, ok_ce = got_root == g["merkle_root"], ce_sha == g["constraint_eval_sha256"]
+    if not (ok_root and ok_ce):
+        raise SystemExit(f"bench: {what}: result differs from the oracle fixture: root {got_root} vs {g['merkle_root']}, "
+                         f"constraint column sha256 {ce_sha} vs {g['constraint_eval_sha256']}")
+    return {"golden": "tests/golden/config3.json", "case": what, "merkle_root": True, "constraint_eval_sha256": True}
+
+
 # ----------------------------------------------------------------------------- CPU arm
 def cpu_sample(log_n, ncols, log_b, steps=1):
     """The restated reference CPU path (oracle/gl_oracle.c, all host threads) on a bounded sample:
@@ -248,9 +271,16 @@ def run_reference(args):
 
 
 def workload_config(args):
-    return {"workload": f"config3: synthetic 2^{args.log_n}-row x {args.ncols}-col Fp trace, iNTT + coset LDE x{1 << LOG_BLOWUP} "
-                        "(bit-reversed) + SHA-256 Merkle commit + constraint eval (32 degree-2 transition constraints, ce_blowup 1)",
-            "log_n": args.log_n, "ncols": args.ncols, "blowup": 1 << LOG_BLOWUP,
+    total_cols = args.ncols * (args.gpus if args.impl != "reference" else 1)
+    shape = (f"2^{args.log_n}-row x {args.ncols}-col" if args.gpus == 1 or args.impl == "reference" else
+             f"2^{args.log_n}-row x {total_cols}-col ({args.ncols} columns per GPU: weak scaling)")
+    sample = (f"; the CPU arm times a 2^{args.cpu_log_n}-row sample of it (1/{1 << (args.log_n - args.cpu_log_n)} of the rows), "
+              "throughput-normalised" if args.impl == "reference" else "")
+    return {"workload": f"config3: synthetic {shape} Fp trace, iNTT + coset LDE x{1 << LOG_BLOWUP} "
+                        "(bit-reversed) + SHA-256 Merkle commit + constraint eval (32 degree-2 transition constraints per "
+                        f"32-column block, ce_blowup 1){sample}",
+            "log_n": args.log_n, "ncols": total_cols, "ncols_per_gpu": args.ncols, "blowup": 1 << LOG_BLOWUP,
+            "timed_rows_log2": args.cpu_log_n if args.impl == "reference" else args.log_n,
             "l2_policy": "inputs (>= 4 GiB per phase) far exceed the 126 MB L2; no explicit flush",
             "parallelism": ("single GPU" if args.gpus == 1 else
                             f"{args.gpus} ranks: one {args.ncols * args.gpus}-column trace, {args.ncols}-column block per rank "
@@ -259,6 +289,210 @@ def workload_config(args):
                              "LDE whose last pass stores each coset block into the owner's row slab over NVLink (CUDA IPC peer "
                              "memory; no all-to-all)") +
                             " for the leaf hash, all-gather of subtree roots and of the partial composition sums")}
+
+
+# ----------------------------------------------------------------------------- verification and extra arms
+def sharded_small_check(ctx, dist, dev, stream, world, rank, args):
+    """N > 1: the sharded commit + partial-composition path of the timed step, on a 2^16-row x 32*N-column instance whose
+    root and constraint column are committed oracle outputs (tests/golden/config3.json)"""
+    import torch
+
+    import ministark_b200 as ms
+    from ministark_b200 import parallel, synth_air
+    log_n, log_b, ncols = 16, LOG_BLOWUP, 32
+    g = golden_entry(log_n, ncols, world)
+    n = 1 << log_n
+    tr = torch.empty((ncols, n), dtype=torch.int64, device=dev)
+    ctx.fill_random(tr, ncols * n, 3000 + rank)
+    sc = parallel.ShardedCommit(parallel.CudaEngine(ctx, dev, stream=stream), dist, log_n, log_b, ncols * world,
+                                fused=False if args.no_fused_exchange else None)
+    sc.transform(tr)
+    root = sc.commit()
+    ev = synth_air.GpuConstraintEval(ctx, log_n, log_b, ncols, dev)
+    ce = torch.empty(n, dtype=torch.int64, device=dev)
+    ev.run(sc.lde, ce)
+    parts = torch.empty((world, n), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(parts, ce)
+    ctx.sum_columns(parts, ce, ms.FP, n, world)
+    ctx.sync()
+    out = check_against_golden(g, root, ce, f"2^{log_n} x {ncols * world} over {world} GPUs (fused exchange: {sc.fused})")
+    sc.close()
+    return out
+
+
+class _FriChannel:
+    """stands in for fri::ProverChannel (src/channel.rs:122-140) in the config-4 sweep: fixed alphas, roots recorded"""
+
+    def __init__(self):
+        self.roots, self.k = [], 0
+
+    def commit_fri_layer(self, root):
+        self.roots.append(root)
+
+    def draw_fri_alpha(self):
+        self.k += 1
+        return (3 + self.k, 5, 7)
+
+
+def _fri_single(prover, cur, log_n, fq, options, channel):
+    """FriProver::build_layers on one GPU (the loop of ministark_b200/prover.py)"""
+    import numpy as np
+    ctx = prover.ctx
+    ff = options.fri_folding_factor
+    log_ff = ff.bit_length() - 1
+    ln = log_n
+    for _ in range(options.fri_num_layers(1 << log_n)):
+        nrows = 1 << (ln - log_ff)
+        leaves, nodes = prover._empty(nrows, 4), prover._empty(nrows, 4)
+        channel.commit_fri_layer(ctx.merkle_commit_rows(cur, ff * fq, nrows, leaves=leaves, nodes=nodes))
+        alpha = channel.draw_fri_alpha()
+        nxt = prover._empty(nrows * fq)
+        ctx.fri_fold(cur, nxt, fq, ln, log_ff, np.array([c * 2**64 % (2**64 - 2**32 + 1) for c in alpha], dtype=np.uint64))
+        cur, ln = nxt, ln - log_ff
+    return cur
+
+
+def extra_arms(args, dist, dev, world, rank):
+    """(1) strong scaling: the FIXED 2^24 x 32 workload over N GPUs, every matrix sharded by LDE coset blocks
+    (ministark_b200/prover_mgpu.py), root and constraint column checked against the full-size oracle fixture;
+    (2) BASELINE config 4: FRI commit phase (every layer: row hashes, tree, fold) of Fq3 codewords 2^20..2^26 on N GPUs;
+    (3) BASELINE config 5 (fib substitute): the whole default_prove of a 2^22-row trace on N GPUs."""
+    import hashlib
+
+    import numpy as np
+    import torch
+
+    import ministark_b200 as ms
+    from ministark_b200 import synth_air
+    from ministark_b200.air import Air, ProofOptions
+    from ministark_b200.examples import fib
+    from ministark_b200.prover import GpuProver
+    if dist is not None:
+        from ministark_b200.prover_mgpu import ShardedProver
+        sp = ShardedProver(dist, dev.index)
+    else:
+        sp = GpuProver(dev.index)
+    ctx = sp.ctx
+
+    def timed(fn, reps):
+        fn()
+        best = None
+        for _ in range(reps):
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = (float(t.item()), out) if best is None or float(t.item()) < best[0] else best
+        return best
+
+    strong = fri = prove = None
+    with torch.cuda.stream(sp.stream):
+        # ---- (1) strong scaling
+        log_n, log_b, ncols = args.log_n, LOG_BLOWUP, args.ncols
+        if dist is not None and (1 << log_b) % world == 0 and ncols % world == 0:
+            n, N = 1 << log_n, 1 << (log_n + log_b)
+            rows_per = N // world
+            full = sp._empty(ncols, n)
+            ctx.fill_random(full, ncols * n, 3000)            # the N = 1 workload; every rank holds the host-side trace
+            prog = synth_air.GpuConstraintEval(ctx, log_n, log_b, ncols, dev).prog
+            ce = sp._empty(n)
+
+            def strong_step():
+                polys = sp._interpolate(full, ms.FP, ncols, log_n)            # 1/N of the columns each + all-gather
+                slab = sp._lde_slab(polys, ms.FP, ncols, log_n, log_b)        # this rank's coset blocks of every column
+                _, root = sp._commit_slab(slab, ms.FP, ncols, rows_per)       # subtree + all-gather of the roots
+                if rank == 0:                                                  # ce_blowup 1: the ce domain is block 0
+                    ctx.eval_constraints_ptrs(prog, ce, log_n, sp._block_ptrs(slab, ms.FP, ncols, rows_per, 0, n),
+                                              [False] * ncols, fq_field=ms.FP, offset=ms.GENERATOR, trace_bitrev=True)
+                dist.broadcast(ce, src=0)
+                return root
+
+            ms_step, root = timed(strong_step, max(1, min(args.steps, 5)))
+            ver = None if args.no_verify else check_against_golden(
+                golden_entry(log_n, ncols, 1), root, ce, f"2^{log_n} x {ncols} over {world} GPUs (strong scaling)")
+            strong = {"workload": f"the N = 1 workload unchanged (2^{log_n} x {ncols}, blow-up {1 << log_b}) over {world} GPUs: iNTT of "
+                                  f"{ncols // world} columns per rank, NCCL all-gather of the coefficients, LDE + leaf hashes + subtree of "
+                                  f"{(1 << log_b) // world} coset block(s) of every column per rank, all-gather of subtree roots, "
+                                  "constraint evaluation on the rank that owns the ce block + broadcast",
+                      "ms_per_step": ms_step, "value": field_ops(log_n, log_b, ncols) / (ms_step / 1000), "unit": "field-ops/s",
+                      "verified": ver}
+            del full, ce
+            torch.cuda.empty_cache()
+
+        # ---- (2) config 4: FRI commit phase of Fq3 codewords
+        fri = []
+        opts = ProofOptions(32, 8, 0, 8, 64)
+        for lg in (20, 22, 24, 26):
+            words = 3 * (1 << lg) // world
+            slab = sp._empty(words)
+            ctx.fill_random(slab, words, 4000 + 16 * lg + rank)
+
+            def fri_step():
+                ch = _FriChannel()
+                if dist is not None:
+                    sp.fri_commit(slab, lg, ms.FQ3, opts, ch)
+                else:
+                    _fri_single(sp, slab, lg, ms.FQ3, opts, ch)
+                return ch.roots
+
+            t_ms, roots = timed(fri_step, 3)
+            rec = {"log_n": lg, "field": "Fq3", "ff": 8, "layers": len(roots), "gpus": world, "ms": t_ms,
+                   "GBps_algorithmic": (24 * (1 << lg) * (1 + 1 / 8)) / (t_ms / 1000) / 1e9, "layer0_root": roots[0].hex()}
+            if dist is not None:                  # the same codeword through the single-GPU loop on rank 0: same roots
+                full = sp._empty(3 * (1 << lg))
+                dist.all_gather_into_tensor(full, slab)
+                if rank == 0:
+                    ch = _FriChannel()
+                    _fri_single(sp, full, lg, ms.FQ3, opts, ch)
+                    if ch.roots != roots:
+                        raise SystemExit(f"bench: sharded FRI roots differ from the single-GPU roots at 2^{lg}")
+                    rec["roots_equal_single_gpu"] = True
+                del full
+            fri.append(rec)
+            del slab
+            torch.cuda.empty_cache()
+
+    # ---- (3) config 5: the whole prover on a 2^22-row examples/fib trace
+    if not args.no_prover and (dist is None or 8 % world == 0):
+        import time
+        log_rows, o5 = args.prove_log_rows, (32, 8, 8, 8, 64)
+        trace, last = fib.gen_trace(8 << log_rows)
+        claim = fib.FibClaim(last)
+        options = ProofOptions(*o5)
+        sp.prove(claim, options, trace)
+        best = None
+        for _ in range(3):
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            proof = sp.prove(claim, options, trace)
+            dt = torch.tensor([time.perf_counter() - t0], device=dev)
+            if dist is not None:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            best = (float(dt.item()), proof) if best is None or float(dt.item()) < best[0] else best
+        dt, proof = best
+        pb = proof.to_bytes()
+        digest = hashlib.sha256(pb).hexdigest()
+        if dist is not None:
+            all_d = [None] * world
+            dist.all_gather_object(all_d, digest)
+            if len(set(all_d)) != 1:
+                raise SystemExit("bench: ranks disagree on the proof bytes")
+        if rank == 0:
+            from oracle import stark_oracle       # the restated verifier as CHECKER of the timed proof, outside the timed region
+            stark_oracle.verify(claim, pb, 20, lambda nn, oo: Air(claim.AirConfig, nn, claim.get_public_inputs(), ProofOptions(*oo)))
+        prove = {"workload": f"examples/fib: 2^{log_rows} rows x 8 Fp columns, ProofOptions{o5} (blow-up 8 so that the 8 coset "
+                             "blocks shard over up to 8 GPUs; the reference example uses blow-up 4), host trace -> proof bytes",
+                 "gpus": world, "seconds": dt, "phases_s": {k: round(v, 5) for k, v in proof.timings.items()},
+                 "proof_bytes": len(pb), "proof_sha256": digest, "verified": True}
+    return strong, fri, prove
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -295,7 +529,7 @@ def run_gpu(args):
         # local iNTT + LDE, all-to-all into row slabs, slab hash + subtree, all-gather of the subtree roots;
         # the composition is a sum over column-local constraint groups: partial sums are all-gathered and added
         from ministark_b200 import parallel
-        sharded = parallel.ShardedCommit(parallel.CudaEngine(ctx, dev), dist, log_n, log_b, ncols * world,
+        sharded = parallel.ShardedCommit(parallel.CudaEngine(ctx, dev, stream=stream), dist, log_n, log_b, ncols * world,
                                          polys=polys, lde=lde, fused=False if args.no_fused_exchange else None)
         if sharded.fused:
             pipe.lde_fn = sharded.lde_columns
@@ -314,11 +548,19 @@ def run_gpu(args):
         """device-resident step, phase by phase (the same calls TraceCommitPipeline.run_resident makes)"""
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         ev[0].record()
-        ctx.ntt_batch_to(trace, polys, ms.FP, log_n, ncols, inverse=True)
-        ev[1].record()
         if sharded is not None and sharded.fused:
-            sharded.lde_columns(0, ncols)          # last pass stores the blocks into the owners' row slabs (peer memory)
+            # the last LDE pass stores its blocks into the owners' row slabs over NVLink: that pass is link-bound, the
+            # others ALU-bound, so the columns go through in chunks — chunk k's store-heavy pass overlaps the peers'
+            # arithmetic of chunk k +- 1 instead of every rank hitting the links at once (SCALE_r01: the chunked
+            # end-to-end path beat the monolithic resident step at N >= 4)
+            ev[1].record()
+            for c0 in range(0, ncols, pipe.chunk):
+                k = min(pipe.chunk, ncols - c0)
+                ctx.ntt_batch_to(trace[c0], polys[c0], ms.FP, log_n, k, inverse=True)
+                sharded.lde_columns(c0, k)
         else:
+            ctx.ntt_batch_to(trace, polys, ms.FP, log_n, ncols, inverse=True)
+            ev[1].record()
             ctx.lde_batch(polys, lde, ms.FP, log_n, log_b, ncols, offset=ms.GENERATOR, bitrev=True)
         ev[2].record()
         root = commit()                                                                # D2H of the 32-byte root
@@ -395,6 +637,25 @@ def run_gpu(args):
         e2e_ms = float(t.item())
     e2e_value = ops / (e2e_ms / 1000)
 
+    # ---- the timed result against the committed oracle fixture: at N = 1 the full-size root and the digest of the
+    #      constraint-evaluation column; at N > 1 the same sharded code path on a 2^16-row instance (fixtures exist for
+    #      32 * N columns, N = 2, 4, 8) — the full-size multi-GPU check is the strong-scaling arm below
+    verified = None
+    if not args.no_verify:
+        if world == 1:
+            verified = check_against_golden(golden_entry(log_n, ncols, 1), root, ce_out, f"2^{log_n} x {ncols}, 1 GPU")
+        else:
+            verified = sharded_small_check(ctx, dist, dev, stream, world, rank, args)
+    strong = fri = sharded_prove = None
+    if world > 1 and not args.no_extra:
+        # free the weak-scaling buffers first: the arms below allocate their own
+        del pipe, evaluator, trace, polys, lde, ce_out, partials, host_trace, host_ce
+        sharded.close()
+        del sharded
+        torch.cuda.empty_cache()
+    if not args.no_extra:
+        strong, fri, sharded_prove = extra_arms(args, dist if world > 1 else None, dev, world, rank)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -437,7 +698,8 @@ def run_gpu(args):
         "e2e": {"value": e2e_value, "unit": "field-ops/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": ncols * n * 8, "d2h_bytes_per_step": 32 + n * 8},
         "roofline": roofline, "cpu_baseline": cpu, "merkle_root": root.hex() if root else None,
-        "full_prove": full_prove,
+        "verified": verified, "full_prove": full_prove,
+        "strong_scaling": strong, "config4_fri": fri, "config5_sharded_prove": sharded_prove,
     }
     print(json.dumps(out))
     if world > 1:
@@ -456,8 +718,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="resident steps only (for ncu captures)")
     ap.add_argument("--no-prover", action="store_true", help="skip the examples/fib full-prove sample")
+    ap.add_argument("--prove-log-rows", type=int, default=22, help="rows of the config-5 (sharded) full-prove sample")
     ap.add_argument("--cpu-prove-log-rows", type=int, default=18, help="--impl reference: rows of the CPU full-prove sample")
     ap.add_argument("--no-fused-exchange", action="store_true", help="N > 1: LDE then NCCL all-to-all instead of the fused scatter")
+    ap.add_argument("--no-verify", action="store_true", help="skip the comparison with the committed oracle fixtures")
+    ap.add_argument("--no-extra", action="store_true", help="skip the strong-scaling, FRI-sweep and sharded-prover arms")
     args = ap.parse_args()
     args.cpu_log_n = min(args.cpu_log_n, args.log_n)
     if args.impl == "reference":

@@ -184,6 +184,8 @@ int ms_ctx_destroy(ms_ctx *c) {
     cudaStreamSynchronize(c->stream);
     c->plans.clear();
     for (auto &t : c->tw_tables) cudaFree(t.second);
+    for (auto &e : c->ptr_tables) cudaFree(e.dev);
+    c->ptr_tables.clear();
     c->tw_tables.clear();
     for (auto &s : c->scratch)
         if (s.ptr) cudaFree(s.ptr);

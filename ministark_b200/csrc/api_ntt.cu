@@ -594,15 +594,34 @@ int ms_lde_batch_scatter(ms_ctx *c, int field, const void *coeffs, size_t in_str
     std::shared_ptr<NttPlanDev> P;
     int rc;
     if ((rc = ntt_get_plan(c, job, &P))) return rc;
-    void *tab;
-    if ((rc = scratch_get(c, 1, (size_t)nb * 16, &tab))) return rc;
+    // the block-pointer table: a small per-context device buffer that is re-uploaded only when its contents change (the
+    // slabs of a run keep their addresses per column chunk), from a host copy that outlives the call — no stream sync
     std::vector<void *> host(2 * nb, nullptr);
     for (unsigned q = 0; q < nb; q++) {
         host[q] = block_ptrs[q];
         host[nb + q] = dup_ptrs ? dup_ptrs[q] : nullptr;
     }
-    MS_CUDA(c, cudaMemcpyAsync(tab, host.data(), (size_t)nb * 16, cudaMemcpyHostToDevice, c->stream));
-    MS_CUDA(c, cudaStreamSynchronize(c->stream));      // host is a stack temporary
+    void *tab = nullptr;
+    for (auto &e : c->ptr_tables)
+        if (e.host == host) tab = e.dev;
+    if (!tab) {
+        if (c->ptr_tables.size() >= 64) {            // bounded: drop the oldest tables
+            MS_CUDA(c, cudaStreamSynchronize(c->stream));
+            for (auto &e : c->ptr_tables) cudaFree(e.dev);
+            c->ptr_tables.clear();
+        }
+        c->ptr_tables.emplace_back();
+        auto &e = c->ptr_tables.back();
+        e.host = host;
+        cudaError_t ce = cudaMalloc(&e.dev, (size_t)nb * 16);
+        if (ce != cudaSuccess) {
+            cudaGetLastError();
+            c->ptr_tables.pop_back();
+            return fail(c, MS_ERR_NOMEM, "pointer table cudaMalloc: %s", cudaGetErrorString(ce));
+        }
+        MS_CUDA(c, cudaMemcpyAsync(e.dev, e.host.data(), (size_t)nb * 16, cudaMemcpyHostToDevice, c->stream));
+        tab = e.dev;
+    }
     LdeScatter sc{(u64 *const *)tab, block_col_stride_elems * field, dup_ptrs ? (u64 *const *)tab + nb : nullptr,
                   dup_col_stride_elems * field};
     return ntt_run(c, *P, (const u64 *)coeffs, in_stride_elems * field, (u64 *)work, work_stride_elems * field, ncols, &sc);

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <deque>
 #include <map>
 #include <memory>
 #include <string>
@@ -30,6 +31,13 @@ struct Scratch {
 
 }  // namespace ms
 
+namespace ms {
+struct PtrTable {
+    std::vector<void *> host;   // block pointers then duplicate pointers (ms_lde_batch_scatter)
+    void *dev = nullptr;
+};
+}  // namespace ms
+
 struct ms_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
@@ -39,6 +47,7 @@ struct ms_ctx {
     ms::Scratch scratch[4];            // grow-only device arenas (0: ntt tmp, 1: staging in, 2: staging out, 3: misc)
     ms::u64 *t4096[2] = {nullptr, nullptr};  // omega_4096^e forward / inverse
     std::map<std::tuple<int, unsigned, int, uint64_t, unsigned, int>, std::shared_ptr<ms::NttPlanDev>> plans;
+    std::deque<ms::PtrTable> ptr_tables;       // cached device copies of LDE scatter pointer tables (deque: stable addresses)
     std::map<unsigned, ms::u64 *> tw_tables;   // log_n -> two-level g_n^e table (4096 + n/4096 words), ntt_plan_tables
 };
 

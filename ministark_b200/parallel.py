@@ -110,6 +110,18 @@ class ShardedCommit:
         if not self.fused:
             self.slab = engine.empty((ncols_total, self.rows_per)) if self.world > 1 else None
 
+    def close(self):
+        """unmap the peers' slabs and free this rank's (fused mode); the object must not be used afterwards"""
+        if self.fused:
+            self.e.sync()
+            self.dist.barrier()                      # nobody is still writing into a slab that is about to go away
+            for r, p in enumerate(self._peer):
+                if r != self.rank:
+                    self.e.ipc_close(p)
+            self.slab = None
+            self.e.free_exportable(self._slab_ptr)
+            self._peer, self.fused = [], False
+
     def transform(self, trace):
         """phase A on the local columns: trace (nloc, n) -> self.polys, self.lde"""
         self.e.intt(trace, self.polys, self.log_n, self.nloc)
@@ -124,8 +136,7 @@ class ShardedCommit:
             self.e.lde(self.polys[c0:c0 + k], self.lde[c0:c0 + k], self.log_n, self.log_b, k)
             return
         if self._need_barrier:           # nobody may still be hashing the slab this LDE is about to overwrite
-            self.e.sync()
-            self.dist.barrier()
+            self.e.rendezvous(self.dist)
             self._need_barrier = False
         n, nblocks = 1 << self.log_n, 1 << self.log_b
         per_rank = nblocks // self.world
@@ -140,8 +151,9 @@ class ShardedCommit:
         if self.world == 1:
             return self.lde
         if self.fused:
-            self.e.sync()                # this rank's stores into the peers' slabs are complete ...
-            self.dist.barrier()          # ... and so are everybody else's into ours
+            # this rank's stores into the peers' slabs are complete and so are everybody else's into ours: a
+            # stream-ordered rendezvous (no host synchronisation)
+            self.e.rendezvous(self.dist)
             self._need_barrier = True
             return self.slab
         per = self.nloc
@@ -182,9 +194,13 @@ class ShardedCommit:
 class CudaEngine:
     """engine over ministark_b200.Context with torch CUDA tensors (int64 storage of the u64 words)."""
 
-    def __init__(self, ctx, device):
+    def __init__(self, ctx, device, stream=None):
+        """stream: the torch stream the Context launches on (its handle was given to ms.Context / set_stream); the
+        collectives are ordered against torch's CURRENT stream, so the two must be the same for stream-ordered
+        rendezvous — otherwise the engine falls back to host synchronisation."""
         import torch
         self.torch, self.ctx, self.device = torch, ctx, device
+        self._stream_handle = None if stream is None else stream.cuda_stream
         self._leaves = self._nodes = None
 
     def empty(self, shape):
@@ -202,6 +218,21 @@ class CudaEngine:
     def sync(self):
         self.ctx.sync()
 
+    def rendezvous(self, dist):
+        """every rank's work enqueued so far is finished before any rank's later work starts — as a one-word NCCL
+        all-reduce ON THE COMPUTE STREAM (kernels before it have completed, incl. their stores into peer memory;
+        kernels after it wait for it), instead of a host barrier that would drain the stream"""
+        if getattr(self, "_flag", None) is None:
+            self._flag = self.torch.zeros(1, dtype=self.torch.int32, device=self.device)
+        if self.torch.cuda.current_stream(self.device).cuda_stream != self.stream_handle():
+            self.ctx.sync()              # the context runs on a foreign stream: fall back to a full synchronisation
+            dist.barrier()
+            return
+        dist.all_reduce(self._flag)
+
+    def stream_handle(self):
+        return getattr(self, "_stream_handle", None)
+
     def alloc_exportable(self, shape):
         """a cudaMalloc'ed buffer (exportable with CUDA IPC, unlike a sub-allocation of torch's caching allocator)
         wrapped as a torch tensor"""
@@ -217,6 +248,13 @@ class CudaEngine:
 
     def ipc_export(self, ptr):
         return self.ctx.ipc_export(ptr)
+
+    def ipc_close(self, ptr):
+        self.ctx.ipc_close(ptr)
+
+    def free_exportable(self, ptr):
+        self._raw = []
+        self.ctx.free(ptr)
 
     def ipc_open(self, handle):
         return self.ctx.ipc_open(handle)

@@ -221,6 +221,50 @@ class ShardedProver(GpuProver):
                 out[k] = row
         return np.concatenate(out) if out else np.zeros(0, dtype=np.uint64)
 
+    def fri_commit(self, slab, log_n, fq, options, channel):
+        """FriProver::build_layers (src/fri.rs:199-231) on a codeword sharded by rows: `slab` holds this rank's
+        2^log_n / G consecutive entries of the bit-reversed codeword.  Per layer: rows of ff entries -> leaf hashes ->
+        subtree -> all-gather of the G subtree roots -> channel; the fold is local (row k needs only row k).  Layers with
+        fewer than 2 rows per rank are gathered once and finished on every rank.  Returns (layers, remainder codeword
+        (replicated), its log size); layers = [(evals, tree, root, rows in the layer, sharded?)]."""
+        ctx, dist, G, rank = self.ctx, self.dist, self.world, self.rank
+        ff = options.fri_folding_factor
+        log_ff = ff.bit_length() - 1
+        layers = []
+        cur, ln, sharded = slab, log_n, True
+        for _ in range(options.fri_num_layers(1 << log_n)):
+            nrows = 1 << (ln - log_ff)
+            if sharded and nrows // G < 2:
+                full = self._empty((1 << ln) * fq)
+                dist.all_gather_into_tensor(full, cur)
+                cur, sharded = full, False
+            if sharded:
+                nloc = nrows // G
+                leaves, nodes = self._empty(nloc, 4), self._empty(nloc, 4)
+                sub = ctx.merkle_commit_rows(cur, ff * fq, nloc, leaves=leaves, nodes=nodes)
+                tree, root = self._finish_tree(sub, leaves, nodes, nloc)
+                channel.commit_fri_layer(root)
+                layers.append((cur, tree, root, nrows, True))
+                alpha = channel.draw_fri_alpha()
+                nxt = self._empty(nloc * fq)
+                off = pow(domain_generator(ln), _brev(rank, self.log_g), P) * _R % P      # ONE * g_(2^ln)^bitrev(rank)
+                ctx.fri_fold(cur, nxt, fq, ln - self.log_g, log_ff,
+                             np.array([_mont(c) for c in _lift(alpha)], dtype=np.uint64), offset=off)
+            else:
+                leaves, nodes = self._empty(nrows, 4), self._empty(nrows, 4)
+                root = ctx.merkle_commit_rows(cur, ff * fq, nrows, leaves=leaves, nodes=nodes)
+                channel.commit_fri_layer(root)
+                layers.append((cur, _Tree(leaves, nodes, nrows), root, nrows, False))
+                alpha = channel.draw_fri_alpha()
+                nxt = self._empty(nrows * fq)
+                ctx.fri_fold(cur, nxt, fq, ln, log_ff, np.array([_mont(c) for c in _lift(alpha)], dtype=np.uint64))
+            cur, ln = nxt, ln - log_ff
+        if sharded:
+            full = self._empty((1 << ln) * fq)
+            dist.all_gather_into_tensor(full, cur)
+            cur = full
+        return layers, cur, ln
+
     # ---- default_prove
     def _prove(self, stark, options, witness):
         ctx, dist, G, rank = self.ctx, self.dist, self.world, self.rank
@@ -378,41 +422,8 @@ class ShardedProver(GpuProver):
         lap("deep_composition")
 
         # ---- FRI (fri.rs:179-249): layers sharded by rows while every rank keeps >= 2 rows of the layer
+        layers, cur, ln = self.fri_commit(deep_slab, log_N, fq, options, channel)
         ff = options.fri_folding_factor
-        log_ff = ff.bit_length() - 1
-        layers = []                 # (evals, tree, root, nrows_total, sharded?)
-        cur, ln, sharded = deep_slab, log_N, True
-        for _ in range(options.fri_num_layers(N)):
-            nrows = 1 << (ln - log_ff)
-            if sharded and nrows // G < 2:
-                full = self._empty((1 << ln) * fq)
-                dist.all_gather_into_tensor(full, cur)
-                cur, sharded = full, False
-            if sharded:
-                nloc = nrows // G
-                leaves, nodes = self._empty(nloc, 4), self._empty(nloc, 4)
-                sub = ctx.merkle_commit_rows(cur, ff * fq, nloc, leaves=leaves, nodes=nodes)
-                tree, root = self._finish_tree(sub, leaves, nodes, nloc)
-                channel.commit_fri_layer(root)
-                layers.append((cur, tree, root, nrows, True))
-                alpha = channel.draw_fri_alpha()
-                nxt = self._empty(nloc * fq)
-                off = pow(domain_generator(ln), _brev(rank, self.log_g), P) * _R % P      # ONE * g_(2^ln)^bitrev(rank)
-                ctx.fri_fold(cur, nxt, fq, ln - self.log_g, log_ff,
-                             np.array([_mont(c) for c in _lift(alpha)], dtype=np.uint64), offset=off)
-            else:
-                leaves, nodes = self._empty(nrows, 4), self._empty(nrows, 4)
-                root = ctx.merkle_commit_rows(cur, ff * fq, nrows, leaves=leaves, nodes=nodes)
-                channel.commit_fri_layer(root)
-                layers.append((cur, _Tree(leaves, nodes, nrows), root, nrows, False))
-                alpha = channel.draw_fri_alpha()
-                nxt = self._empty(nrows * fq)
-                ctx.fri_fold(cur, nxt, fq, ln, log_ff, np.array([_mont(c) for c in _lift(alpha)], dtype=np.uint64))
-            cur, ln = nxt, ln - log_ff
-        if sharded:
-            full = self._empty((1 << ln) * fq)
-            dist.all_gather_into_tensor(full, cur)
-            cur, sharded = full, False
         rem_size = 1 << ln
         if rem_size > options.fri_max_remainder_coeffs * beta:
             raise ProvingError("remainder domain too large")

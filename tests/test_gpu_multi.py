@@ -28,7 +28,7 @@ def _worker(rank, world, port, log_n, log_b, ncols, q, fused=None):
         torch.cuda.set_stream(stream)
         ctx = ms.Context(rank, stream=stream.cuda_stream)
         full = orc.rand_matrix(ncols, 1 << log_n, 1, seed=88)
-        sc = parallel.ShardedCommit(parallel.CudaEngine(ctx, torch.device("cuda", rank)), dist, log_n, log_b, ncols, fused=fused)
+        sc = parallel.ShardedCommit(parallel.CudaEngine(ctx, torch.device("cuda", rank), stream=stream), dist, log_n, log_b, ncols, fused=fused)
         assert sc.fused == (fused is not False)
         local = torch.from_numpy(full[sc.lo:sc.hi].view(np.int64).copy()).cuda(rank)
         roots = []

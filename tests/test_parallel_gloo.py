@@ -87,6 +87,9 @@ class PeerOracleEngine(OracleEngine):
     def sync(self):
         pass
 
+    def rendezvous(self, dist):
+        dist.barrier()              # the CPU engine is synchronous: a host barrier is the whole rendezvous
+
     def _store(self, addr, words):
         local = bool(addr & self.LOCAL)
         addr &= self.LOCAL - 1
