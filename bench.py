@@ -463,7 +463,7 @@ def extra_arms(args, dist, dev, world, rank):
     if not args.no_prover and (dist is None or 8 % world == 0):
         import time
         log_rows, o5 = args.prove_log_rows, (32, 8, 8, 8, 64)
-        trace, last = fib.gen_trace(8 << log_rows)
+        trace, last = fib.gen_trace(8 << log_rows, pinned=True)     # page-locked columns, like the reference's GpuAllocator
         claim = fib.FibClaim(last)
         options = ProofOptions(*o5)
         sp.prove(claim, options, trace)

@@ -106,6 +106,86 @@ class _ShardedTree:
         self.leaves, self.nodes, self.n_local, self.n_total, self.top = leaves, nodes, n_local, n_total, top
 
 
+class _FetchPlan:
+    """The query phase needs ~30 LDE rows per matrix, ~30 rows per FRI layer and a few hundred path digests, each living
+    on the rank that owns its row.  Requests are collected first, every rank then fetches what it owns with one device
+    gather per matrix / tree, and ONE all-gather of the (small) pieces gives every rank everything."""
+
+    def __init__(self, prover):
+        self.p = prover
+        self.groups = []          # (fetch(list of local indices) -> sequence of byte strings / arrays, [(item, local index)])
+        self.nitems = 0
+        self.literal = {}
+        self.data = None
+
+    def _new(self):
+        self.nitems += 1
+        return self.nitems - 1
+
+    def rows(self, gather_local, n_local, positions):
+        """handles of the rows at global `positions`; gather_local(list of local row ids) -> (k, words) array"""
+        mine, handles = [], []
+        for p in positions:
+            h = self._new()
+            handles.append(h)
+            if p // n_local == self.p.rank:
+                mine.append((h, p - self.p.rank * n_local))
+        if mine:
+            self.groups.append((lambda loc, f=gather_local: [np.asarray(r, dtype=np.uint64).copy() for r in f(loc)], mine))
+        return handles
+
+    def view(self, tree, positions):
+        """handles of a MerkleView over a sharded tree: (path handles, initial-leaf handles, sibling-leaf handles, height)"""
+        init, sib, path = merkle_walk(tree.n_total, positions)
+        leaf_mine, node_mine = [], []
+
+        def leaf(i):
+            h = self._new()
+            owner, loc = divmod(i, tree.n_local)
+            if owner == self.p.rank:
+                leaf_mine.append((h, loc))
+            return h
+
+        def node(k):
+            h = self._new()
+            owner, loc = node_owner(k, self.p.log_g)
+            if owner is None:
+                self.literal[h] = tree.top[loc] if loc else bytes(32)     # heap index 0: the unused default digest
+            elif owner == self.p.rank:
+                node_mine.append((h, loc))
+            return h
+
+        hi, hs, hp = [leaf(i) for i in init], [leaf(i) for i in sib], [node(k) for k in path]
+        dev = self.p.device
+
+        def fetch(t):
+            return lambda loc: [r.tobytes() for r in t.index_select(0, torch.tensor(loc, dtype=torch.int64, device=dev)).cpu().numpy()]
+
+        if leaf_mine:
+            self.groups.append((fetch(tree.leaves), leaf_mine))
+        if node_mine:
+            self.groups.append((fetch(tree.nodes), node_mine))
+        return hp, hi, hs, tree.n_total.bit_length() - 1
+
+    def execute(self):
+        mine = dict(self.literal) if self.p.rank == 0 else {}
+        for fn, lst in self.groups:
+            for (h, _), v in zip(lst, fn([loc for _, loc in lst])):
+                mine[h] = v
+        self.data = {}
+        for part in self.p._all_gather_objects(mine):
+            self.data.update(part)
+        self.data.update(self.literal)
+        assert len(self.data) == self.nitems, "a queried row or digest has no owner"
+
+    def get_rows(self, handles):
+        return np.concatenate([self.data[h] for h in handles]) if handles else np.zeros(0, dtype=np.uint64)
+
+    def get_view(self, v):
+        hp, hi, hs, height = v
+        return MerkleView([self.data[h] for h in hp], [self.data[h] for h in hi], [self.data[h] for h in hs], height)
+
+
 class ShardedProver(GpuProver):
     def __init__(self, dist, device):
         super().__init__(device)
@@ -129,9 +209,10 @@ class ShardedProver(GpuProver):
         return out
 
     # ---- building blocks
-    def _interpolate(self, evals, field, ncols, log_n):
+    def _interpolate(self, evals, field, ncols, log_n, from_host=False):
         """Matrix::interpolate (src/matrix.rs:101-116): the inverse transforms are split by columns, the coefficient
-        columns all-gathered — every rank ends up with the whole (ncols, n) coefficient matrix."""
+        columns all-gathered — every rank ends up with the whole (ncols, n) coefficient matrix.  from_host: `evals` is a
+        host matrix of which only this rank's column block is uploaded."""
         n, G = 1 << log_n, self.world
         if ncols < G:
             polys = self._empty(ncols, n * field)
@@ -141,7 +222,11 @@ class ShardedProver(GpuProver):
         pad = self._empty(G * per, n * field)
         lo, hi = min(self.rank * per, ncols), min((self.rank + 1) * per, ncols)
         if hi > lo:
-            self.ctx.ntt_batch_to(evals[lo], pad[lo], field, log_n, hi - lo, inverse=True)
+            if from_host:
+                pad[lo:hi].copy_(self._to_device(evals[lo:hi]))
+                self.ctx.ntt_batch(pad[lo], field, log_n, hi - lo, inverse=True)
+            else:
+                self.ctx.ntt_batch_to(evals[lo], pad[lo], field, log_n, hi - lo, inverse=True)
         self.dist.all_gather_into_tensor(pad.view(-1), pad[self.rank * per:(self.rank + 1) * per].reshape(-1))
         return pad[:ncols]
 
@@ -172,54 +257,6 @@ class ShardedProver(GpuProver):
 
     def _block_ptrs(self, slab, field, ncols, rows_per, j, n):
         return [slab.data_ptr() + (c * rows_per + j * n) * field * 8 for c in range(ncols)]
-
-    def _sharded_view(self, tree, positions):
-        """MerkleTreeImpl::prove over the sharded tree: every rank fetches the digests it owns, the pieces are
-        all-gathered (a few hundred digests), every rank assembles the same MerkleView."""
-        init, sib, path = merkle_walk(tree.n_total, positions)
-        want = [("leaf", i) for i in init] + [("leaf", i) for i in sib] + [("node", k) for k in path]
-        mine_idx, mine_pos, mine_is_leaf = [], [], []
-        out = [None] * len(want)
-        for pos, (kind, i) in enumerate(want):
-            if kind == "leaf":
-                owner, loc = divmod(i, tree.n_local)
-            else:
-                owner, loc = node_owner(i, self.log_g)
-                if owner is None:
-                    out[pos] = tree.top[loc] if loc else bytes(32)
-                    continue
-            if owner == self.rank:
-                mine_idx.append(loc)
-                mine_pos.append(pos)
-                mine_is_leaf.append(kind == "leaf")
-        got = []
-        if mine_idx:
-            sel = torch.tensor(mine_idx, dtype=torch.int64, device=self.device)
-            lv = tree.leaves.index_select(0, sel).cpu().numpy()
-            nd = tree.nodes.index_select(0, sel.clamp(max=tree.nodes.shape[0] - 1)).cpu().numpy()
-            for k, pos in enumerate(mine_pos):
-                got.append((pos, (lv[k] if mine_is_leaf[k] else nd[k]).tobytes()))
-        for part in self._all_gather_objects(got):
-            for pos, b in part:
-                out[pos] = b
-        assert all(o is not None for o in out)
-        a, b = len(init), len(init) + len(sib)
-        height = tree.n_total.bit_length() - 1
-        return MerkleView(out[b:], out[:a], out[a:b], height)
-
-    def _gather_rows_sharded(self, gather_local, n_local, positions):
-        """rows at global `positions` (sorted, distinct), each fetched by its owner; returns them in position order"""
-        mine = [(k, p - self.rank * n_local) for k, p in enumerate(positions) if p // n_local == self.rank]
-        part = []
-        if mine:
-            rows = gather_local([loc for _, loc in mine])
-            rows = np.asarray(rows, dtype=np.uint64).reshape(len(mine), -1)
-            part = [(k, rows[i].copy()) for i, (k, _) in enumerate(mine)]
-        out = [None] * len(positions)
-        for p in self._all_gather_objects(part):
-            for k, row in p:
-                out[k] = row
-        return np.concatenate(out) if out else np.zeros(0, dtype=np.uint64)
 
     def fri_commit(self, slab, log_n, fq, options, channel):
         """FriProver::build_layers (src/fri.rs:199-231) on a codeword sharded by rows: `slab` holds this rank's
@@ -311,8 +348,13 @@ class ShardedProver(GpuProver):
         host_base = trace.base_columns()
         if tuple(host_base.shape) != (nbase, n):
             raise ProvingError(f"expected {nbase} base columns of {n} rows")
-        base = self._to_device(host_base)
-        base_polys = self._interpolate(base, FP, nbase, log_n)
+        needs_full_base = next_ > 0          # extension columns are built from the whole base trace (on every rank)
+        if needs_full_base or nbase < G or (isinstance(host_base, torch.Tensor) and host_base.is_cuda):
+            base = self._to_device(host_base)
+            base_polys = self._interpolate(base, FP, nbase, log_n)
+        else:
+            base = None
+            base_polys = self._interpolate(host_base, FP, nbase, log_n, from_host=True)
         base_slab = self._lde_slab(base_polys, FP, nbase, log_n, log_b)
         base_tree, base_root = self._commit_slab(base_slab, FP, nbase, rows_per)
         channel.commit_base_trace(base_root)
@@ -444,33 +486,38 @@ class ShardedProver(GpuProver):
 
         # ---- queries (fri.rs:151-177, trace.rs:115-157): rows and path digests come from the ranks that own them
         positions = channel.get_fri_query_positions()
-        fri_layers, folded = [], positions
+        pos_sorted = sorted(set(positions))
+        plan = _FetchPlan(self)
+        pending, folded = [], positions
         for evals, tree, root, nrows, was_sharded in layers:
             folded = sorted(set(p // ff for p in folded))
             if was_sharded:
                 nloc = nrows // G
-                rows = self._gather_rows_sharded(lambda loc, e=evals, k=nloc: ctx.gather_rows_rowmajor(e, ff * fq, k, loc), nloc, folded)
-                view = self._sharded_view(tree, folded)
+                hr = plan.rows(lambda loc, e=evals, k=nloc: ctx.gather_rows_rowmajor(e, ff * fq, k, loc), nloc, folded)
+                pending.append((root, hr, plan.view(tree, folded), None))
             else:
                 rows = ctx.gather_rows_rowmajor(evals, ff * fq, nrows, folded)
-                view = self._view(tree, folded)
-            fri_layers.append(LayerProof(_canon_rows(rows, fq), view, root))
-        fri_proof = FriProof(fri_layers, channel.fri_remainder_coeffs)
-        pos_sorted = sorted(set(positions))
+                pending.append((root, None, None, (rows, self._view(tree, folded))))
 
         def trace_rows(slab, field, ncols):
             # Queries::new keeps the caller's position order (sorted, deduplicated by draw_queries)
-            got = self._gather_rows_sharded(lambda loc: ctx.gather_rows(slab, field, rows_per, ncols, loc, col_stride=rows_per),
-                                            rows_per, positions)
-            return got
+            return plan.rows(lambda loc: ctx.gather_rows(slab, field, rows_per, ncols, loc, col_stride=rows_per), rows_per, positions)
 
+        h_base, h_comp = trace_rows(base_slab, FP, nbase), trace_rows(comp_slab, fq, ce_blowup)
+        h_ext = trace_rows(ext_slab, fq, next_) if next_ else None
+        v_base, v_comp = plan.view(base_tree, pos_sorted), plan.view(comp_tree, pos_sorted)
+        v_ext = plan.view(ext_tree, pos_sorted) if next_ else None
+        plan.execute()
+        fri_layers = []
+        for root, hr, hv, direct in pending:
+            rows, view = (plan.get_rows(hr), plan.get_view(hv)) if direct is None else direct
+            fri_layers.append(LayerProof(_canon_rows(rows, fq), view, root))
+        fri_proof = FriProof(fri_layers, channel.fri_remainder_coeffs)
         queries = Queries(
-            _canon_rows(trace_rows(base_slab, FP, nbase), 1),
-            _canon_rows(trace_rows(ext_slab, fq, next_), fq) if next_ else [],
-            _canon_rows(trace_rows(comp_slab, fq, ce_blowup), fq),
-            self._sharded_view(base_tree, pos_sorted),
-            self._sharded_view(ext_tree, pos_sorted) if next_ else None,
-            self._sharded_view(comp_tree, pos_sorted))
+            _canon_rows(plan.get_rows(h_base), 1),
+            _canon_rows(plan.get_rows(h_ext), fq) if next_ else [],
+            _canon_rows(plan.get_rows(h_comp), fq),
+            plan.get_view(v_base), plan.get_view(v_ext) if next_ else None, plan.get_view(v_comp))
         lap("queries")
         timings["total"] = time.perf_counter() - t_all
         return Proof(options, n, channel.base_trace_commitment, channel.extension_trace_commitment,
