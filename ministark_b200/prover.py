@@ -172,12 +172,22 @@ class GpuProver:
         timings = {}
         t_all = t0 = time.perf_counter()
 
+        # NVTX range per prover phase (visible to nsys / ncu --nvtx): the range of phase k is closed and the range of
+        # phase k + 1 opened where the reference prints its per-phase timings (src/prover.rs:40-170)
+        phases = ["init_air", "base_trace_commitment", "extension_trace_commitment", "constraint_eval",
+                  "composition_trace_commitment", "deep_composition", "fri", "proof_of_work", "queries"]
+        torch.cuda.nvtx.range_push("prove:" + phases[0])
+
         def lap(name):
             nonlocal t0
             ctx.sync()
             t = time.perf_counter()
             timings[name] = t - t0
             t0 = t
+            torch.cuda.nvtx.range_pop()
+            k = phases.index(name) + 1
+            if k < len(phases):
+                torch.cuda.nvtx.range_push("prove:" + phases[k])
 
         trace = stark.generate_trace(witness)
         n = len(trace)

@@ -1,0 +1,146 @@
+//! The AIR of examples/fib (examples/fib/main.rs:54-172) stated against the reference's public items, and one proof.
+//! 8 columns hold 8 consecutive terms of v_k = v_(k-2) * v_(k-1) (v_0 = 1, v_1 = 2) per row.
+use ark_ff::One;
+use ark_poly::{EvaluationDomain, Radix2EvaluationDomain};
+use ark_serialize::CanonicalSerialize;
+use ministark::air::AirConfig;
+use ministark::challenges::Challenges;
+use ministark::constraints::{AlgebraicItem, Constraint, ExecutionTraceColumn};
+use ministark::hash::{HashFn, Sha256HashFn};
+use ministark::hints::Hints;
+use ministark::merkle::MatrixMerkleTreeImpl;
+use ministark::random::{PublicCoin, PublicCoinImpl};
+use ministark::stark::Stark;
+use ministark::utils::{FieldVariant, SerdeOutput};
+use ministark::{Air, Matrix, ProofOptions, Trace};
+use ministark_gpu::fields::p18446744069414584321::ark::Fp;
+use num_traits::Pow;
+use sha2::{Digest as _, Sha256};
+
+pub struct FibTrace(Matrix<Fp>);
+
+impl Trace for FibTrace {
+    type Fp = Fp;
+    type Fq = Fp;
+    fn len(&self) -> usize {
+        self.0.num_rows()
+    }
+    fn base_columns(&self) -> &Matrix<Self::Fp> {
+        &self.0
+    }
+}
+
+pub struct FibAir;
+
+impl AirConfig for FibAir {
+    const NUM_BASE_COLUMNS: usize = 8;
+    type Fp = Fp;
+    type Fq = Fp;
+    type PublicInputs = Fp;
+
+    fn gen_hints(_n: usize, claimed: &Fp, _: &Challenges<Fp>) -> Hints<Fp> {
+        Hints::new(vec![(0, *claimed)])
+    }
+
+    fn constraints(trace_len: usize) -> Vec<Constraint<FieldVariant<Fp, Fp>>> {
+        use AlgebraicItem::*;
+        let xs = Radix2EvaluationDomain::<Fp>::new(trace_len).unwrap();
+        let first = Constant(FieldVariant::Fp(xs.element(0)));
+        let last = Constant(FieldVariant::Fp(xs.element(trace_len - 1)));
+        let one = Constant(FieldVariant::Fp(Fp::one()));
+        // the first row holds v_0 .. v_7
+        let mut v = vec![one, one + one];
+        for i in 2..8 {
+            let next = &v[i - 2] * &v[i - 1];
+            v.push(next);
+        }
+        let mut cs = Vec::new();
+        for (i, vi) in v.into_iter().enumerate() {
+            cs.push((i.curr() - vi) / (X - first));
+        }
+        cs.push((7.curr() - Hint(0)) / (X - last));
+        let all_rows_but_last = (X - last) / (X.pow(trace_len) - one);
+        let step = vec![
+            0.next() - 6.curr() * 7.curr(),
+            1.next() - 7.curr() * 0.next(),
+            2.next() - 0.next() * 1.next(),
+            3.next() - 1.next() * 2.next(),
+            4.next() - 2.next() * 3.next(),
+            5.next() - 3.next() * 4.next(),
+            6.next() - 4.next() * 5.next(),
+            7.next() - 5.next() * 6.next(),
+        ];
+        for c in step {
+            cs.push(c * &all_rows_but_last);
+        }
+        cs.into_iter().map(Constraint::new).collect()
+    }
+}
+
+pub struct FibClaim(Fp);
+
+impl Stark for FibClaim {
+    type Fp = Fp;
+    type Fq = Fp;
+    type AirConfig = FibAir;
+    type Digest = SerdeOutput<Sha256>;
+    type PublicCoin = PublicCoinImpl<Fp, Sha256HashFn>;
+    type MerkleTree = MatrixMerkleTreeImpl<Sha256HashFn>;
+    type Witness = FibTrace;
+    type Trace = FibTrace;
+
+    fn get_public_inputs(&self) -> Fp {
+        self.0
+    }
+    fn generate_trace(&self, witness: FibTrace) -> FibTrace {
+        witness
+    }
+    fn gen_public_coin(&self, air: &Air<FibAir>) -> Self::PublicCoin {
+        let mut seed = Vec::new();
+        air.public_inputs().serialize_compressed(&mut seed).unwrap();
+        air.trace_len().serialize_compressed(&mut seed).unwrap();
+        air.options().serialize_compressed(&mut seed).unwrap();
+        PublicCoinImpl::new(Sha256HashFn::hash_chunks([&*seed]))
+    }
+}
+
+fn gen_trace(num_rows: usize) -> (FibTrace, Fp) {
+    let mut rows: Vec<Vec<Fp>> = Vec::with_capacity(num_rows);
+    let mut v = vec![Fp::one(), Fp::one() + Fp::one()];
+    for i in 2..8 {
+        let t = v[i - 2] * v[i - 1];
+        v.push(t);
+    }
+    for _ in 0..num_rows {
+        rows.push(v.clone());
+        let mut w = vec![v[6] * v[7]];
+        w.push(v[7] * w[0]);
+        for i in 2..8 {
+            let t = w[i - 2] * w[i - 1];
+            w.push(t);
+        }
+        v = w;
+    }
+    let last = rows[num_rows - 1][7];
+    (FibTrace(Matrix::from_rows(rows)), last)
+}
+
+/// proof bytes for 2^7 rows with the example's own options; tests/golden/golden_r01.json holds what the restatement
+/// produces for the same claim ("fib_2p7_rows_proof_sha256")
+pub fn proof_vector() -> String {
+    let options = ProofOptions::new(32, 4, 8, 8, 64);
+    let (trace, last) = gen_trace(1 << 7);
+    let claim = FibClaim(last);
+    let proof = pollster::block_on(claim.prove(options, trace)).expect("prover failed");
+    let mut bytes = Vec::new();
+    proof.serialize_compressed(&mut bytes).unwrap();
+    let digest: String = Sha256::digest(&bytes).iter().map(|b| format!("{b:02x}")).collect();
+    claim.verify(proof, 30).expect("verification failed");
+    use ark_ff::PrimeField;
+    format!(
+        "\"fib_proof\": {{\"log_rows\": 7, \"options\": [32,4,8,8,64], \"claim_canonical\": {}, \"proof_len\": {}, \"proof_sha256\": \"{}\", \"pow_nonce_rule\": \"serial find: smallest nonce >= 1\"}}",
+        last.into_bigint().0[0],
+        bytes.len(),
+        digest
+    )
+}
