@@ -21,7 +21,7 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 
 def short(name):
     name = re.sub(r"\(.*", "", name)
-    name = name.replace("void ", "").replace("msntt::", "").replace("ms::", "")
+    name = name.replace("void ", "").replace("msntt::", "").replace("ms::", "").replace("<unnamed>::", "").replace("unnamed>::", "")
     return name.strip()
 
 
@@ -65,7 +65,7 @@ def main():
         md.append(f"| `{name}` | {cnt} | {ms:.3f} | {100 * ms / total:.1f}% | {rd / 1e9:.2f} | {wr / 1e9:.2f} | {(rd + wr) / 1e6 / max(ms, 1e-9):.0f} |")
     md.append(f"| **total** | {sum(a[0] for a in agg.values())} | {total:.3f} | 100% | | | |")
     # per-launch list of the NTT passes of the LDE (the three longest ntt_pass launches)
-    ntt = [r for r in step if r[1].startswith("ntt_pass_kernel")]
+    ntt = [r for r in step if r[1].startswith("ntt_pass_kernel") or "ntt_tma_kernel" in r[1]]
     lde = sorted(ntt, key=lambda r: -r[2])[:3]
     md += ["", "## LDE passes (3 launches, all 32 columns x 8 cosets each)", "",
            "| launch | device ms | DRAM read GB | DRAM write GB | algorithmic GB (SURVEY §8d share) |", "|---|---:|---:|---:|---:|"]
@@ -92,11 +92,18 @@ def main():
             "smsp__issue_active.avg.pct_of_peak_sustained_active",
             "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
             "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+            "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+            "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+            "sm__inst_executed_pipe_tma.sum",
             "sm__inst_executed_pipe_lsu.sum.pct_of_peak_sustained_active",
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
             "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
-    md = [f"# ncu --set full summaries `{tag}` (2^22-row instance of the same pipeline)", ""]
+    md = [f"# ncu --set full summaries `{tag}`" + (" (NTT kernels: 2^24-point transforms, 4 columns x 8 cosets, profiles/exp_ntt_r02.py prof; hash / "
+          "evaluator kernels: 2^22-row instance of the bench step)" if tag.startswith("r02") else " (2^22-row instance of the same pipeline)"), ""]
     for rep in (f"prof_ntt_lde_{tag}.ncu-rep", f"prof_hash_eval_{tag}.ncu-rep"):
         path = os.path.join(OUT, rep)
         if not os.path.exists(path):
