@@ -364,6 +364,8 @@ int ntt_run(ms_ctx *c, NttPlanDev &P, const u64 *in, size_t in_cs, u64 *out, siz
                     p.out_col_stride = sc->block_col_stride_words;
                     p.out_dup_ptr = sc->dup_ptr;
                     p.dup_col_stride = sc->dup_col_stride_words;
+                    p.host_cos_ptr = sc->host_block_ptr;
+                    p.host_dup_ptr = sc->host_dup_ptr;
                 }
             } else if (m == 1) {
                 pin = src;
@@ -623,7 +625,7 @@ int ms_lde_batch_scatter(ms_ctx *c, int field, const void *coeffs, size_t in_str
         tab = e.dev;
     }
     LdeScatter sc{(u64 *const *)tab, block_col_stride_elems * field, dup_ptrs ? (u64 *const *)tab + nb : nullptr,
-                  dup_col_stride_elems * field};
+                  dup_col_stride_elems * field, host.data(), dup_ptrs ? host.data() + nb : nullptr};
     return ntt_run(c, *P, (const u64 *)coeffs, in_stride_elems * field, (u64 *)work, work_stride_elems * field, ncols, &sc);
 }
 

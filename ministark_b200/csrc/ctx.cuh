@@ -103,6 +103,8 @@ struct LdeScatter {
     size_t block_col_stride_words;
     u64 *const *dup_ptr;
     size_t dup_col_stride_words;
+    void *const *host_block_ptr = nullptr;   // the same tables on the host (2^log_blowup entries each; dup may be null)
+    void *const *host_dup_ptr = nullptr;
 };
 int ntt_run(ms_ctx *c, NttPlanDev &plan, const u64 *in, size_t in_col_stride_words, u64 *out,
             size_t out_col_stride_words, unsigned ncols, const LdeScatter *scatter = nullptr);

@@ -61,6 +61,10 @@ struct PassParams {
     u64 *const *out_cos_ptr = nullptr;
     u64 *const *out_dup_ptr = nullptr;
     u64 dup_col_stride = 0;              // words
+    // the same two tables as HOST arrays (valid for the duration of the launch call): the TMA pipeline encodes one
+    // tensor map per destination block from them
+    void *const *host_cos_ptr = nullptr;
+    void *const *host_dup_ptr = nullptr;
 };
 
 struct Tables {

@@ -100,6 +100,16 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *tm) {
 // the 16-byte chunk index is XORed with row % 8.
 __host__ __device__ constexpr u32 swz(u32 row, u32 e) { return row * 16 + ((((e >> 1) ^ (row & 7))) << 1) + (e & 1); }
 
+constexpr int kMaxScatterCos = 16;
+// LDE scatter (multi-GPU fused exchange): one tensor map per destination coset block (possibly PEER memory mapped with
+// CUDA IPC: the TMA store goes out over NVLink) and per optional second copy
+struct ScatterMaps {
+    CUtensorMap out[kMaxScatterCos];
+    CUtensorMap dup[kMaxScatterCos];
+    u32 dup_mask;        // bit q: block q has a second destination
+    u32 log_chunks;      // log2(4096-word chunks per coset block)
+};
+
 struct TmaArgs {
     u32 ncols;
     u32 log_ncos;     // cosets per column (LDE), 0 otherwise
@@ -218,10 +228,10 @@ __device__ __forceinline__ void coords(const TmaArgs &A, u32 u, u32 col, Coord &
 }
 
 // TYPE 0: strided pass, 1: contiguous (last, bit-reversed) pass.  G consumer groups of 8 warps.
+// scat != nullptr (contiguous pass only): every 4096-word chunk is stored through the tensor map of its coset block.
 template <int TYPE, bool INV, bool BITREV, bool HAS_PRE, int G>
-__global__ void __launch_bounds__(32 + 256 * G, 1)
-ntt_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
-               const __grid_constant__ CUtensorMap tm_tw, const __grid_constant__ CUtensorMap tm_pre, const TmaArgs A) {
+__device__ __forceinline__ void ntt_tma_body(const CUtensorMap &tm_in, const CUtensorMap &tm_out, const CUtensorMap &tm_tw,
+                                             const CUtensorMap &tm_pre, const TmaArgs &A, const ScatterMaps *scat) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     constexpr bool HAS_TW = TYPE == 0;
     constexpr u32 NW = 8 * G;
@@ -328,7 +338,14 @@ ntt_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
             if (si < li && mbar_test(comp_bar(ss), sk & 1)) {
                 Coord ci, co, ct, cp;
                 coords<TYPE>(A, su, scol, ci, co, ct, cp);
-                tma_store4(&tm_out, smem_u32(stages + (size_t)ss * kTileWords), co.c0, co.c1, co.c2, co.c3);
+                if (scat) {
+                    const u32 cos = su >> scat->log_chunks, within = su & ((1u << scat->log_chunks) - 1);
+                    tma_store4(&scat->out[cos], smem_u32(stages + (size_t)ss * kTileWords), 0, (int)(256 * within), (int)scol, 0);
+                    if ((scat->dup_mask >> cos) & 1)
+                        tma_store4(&scat->dup[cos], smem_u32(stages + (size_t)ss * kTileWords), 0, (int)(256 * within), (int)scol, 0);
+                } else {
+                    tma_store4(&tm_out, smem_u32(stages + (size_t)ss * kTileWords), co.c0, co.c1, co.c2, co.c3);
+                }
                 tma_commit();
                 tma_wait_read<1>();   // every store but the one just issued has finished reading its stage
                 sdone = si;
@@ -393,6 +410,20 @@ ntt_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         }
     }
     (void)i;
+}
+
+template <int TYPE, bool INV, bool BITREV, bool HAS_PRE, int G>
+__global__ void __launch_bounds__(32 + 256 * G, 1)
+ntt_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+               const __grid_constant__ CUtensorMap tm_tw, const __grid_constant__ CUtensorMap tm_pre, const TmaArgs A) {
+    ntt_tma_body<TYPE, INV, BITREV, HAS_PRE, G>(tm_in, tm_out, tm_tw, tm_pre, A, nullptr);
+}
+
+// the last pass of a multi-GPU LDE: contiguous tiles in, one destination per coset block out
+template <int G>
+__global__ void __launch_bounds__(32 + 256 * G, 1)
+ntt_tma_scatter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ ScatterMaps scat, const TmaArgs A) {
+    ntt_tma_body<1, false, true, false, G>(tm_in, tm_in, tm_in, tm_in, A, &scat);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------
@@ -470,6 +501,33 @@ bool launch_inst(const CUtensorMap &mi, const CUtensorMap &mo, const CUtensorMap
     return true;
 }
 
+template <int G>
+bool launch_scatter(const CUtensorMap &mi, const ScatterMaps &sm, TmaArgs A, cudaStream_t stream) {
+    auto kern = ntt_tma_scatter_kernel<G>;
+    int dev = 0, max_smem = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t fixed = 2048 + 8 * (2 * kMaxStages + 6);
+    int ns = (int)(((size_t)max_smem - fixed) / kTileBytes);
+    if (ns > g_max_stages) ns = g_max_stages;
+    if (ns > kMaxStages) ns = kMaxStages;
+    if (ns < 3) return false;
+    A.nstages = (u32)ns;
+    static bool attr_set[64] = {false};
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    unsigned grid = (unsigned)sms;
+    if (A.units < grid) grid = A.units;
+    kern<<<grid, 32 + 256 * G, fixed + (size_t)ns * kTileBytes, stream>>>(mi, sm, A);
+    return true;
+}
+
 template <int TYPE, bool INV, bool BITREV, bool HAS_PRE>
 bool launch_g(const CUtensorMap &mi, const CUtensorMap &mo, const CUtensorMap &mt, const CUtensorMap &mp, const TmaArgs &A,
               cudaStream_t stream) {
@@ -492,7 +550,10 @@ bool launch_pass_tma(const PassParams &p, const Tables &t, bool inverse, const u
     if (!g_enabled) return false;
     static const bool env_off = [] { const char *e = getenv("MS_NTT_TMA"); return e && e[0] == '0'; }();
     if (env_off) return false;
-    if (p.log_r != 8 || p.log_w != 4 || p.estride != 1 || p.lanes != 1 || p.out_cos_ptr || p.has_post) return false;
+    if (p.log_r != 8 || p.log_w != 4 || p.estride != 1 || p.lanes != 1 || p.has_post) return false;
+    if (p.out_cos_ptr && !p.host_cos_ptr) return false;
+    static const bool scatter_off = [] { const char *e = getenv("MS_NTT_TMA_SCATTER"); return e && e[0] == '0'; }();
+    if (p.out_cos_ptr && scatter_off) return false;
     const u64 N = p.n_mask + 1;
     const u32 ncos = p.ncos;
     if ((u64)ntiles * ncos * ncols < 1024) return false;   // too little work for 148 persistent CTAs
@@ -547,11 +608,34 @@ bool launch_pass_tma(const PassParams &p, const Tables &t, bool inverse, const u
     }
     if (contig) {
         if (!p.bitrev_digit || p.has_outer || p.has_pre || inverse || p.in_rs != 1 || p.out_rs != 1 || in != out) return false;
-        if (p.in_col_stride != p.out_col_stride) return false;
-        if (ncos > 1 && (p.in_cos_stride != N || p.out_cos_stride != N)) return false;
+        if (!p.out_cos_ptr && p.in_col_stride != p.out_col_stride) return false;
+        if (ncos > 1 && (p.in_cos_stride != N || (!p.out_cos_ptr && p.out_cos_stride != N))) return false;
         const u64 words = N * ncos;   // per column
         A.units = (u32)(words / 4096);
         A.log_ncos = 0;
+        if (p.out_cos_ptr) {
+            // scatter: chunks are read from the work buffer (in) and stored through per-block tensor maps
+            if (ncos > (u32)kMaxScatterCos || N < 4096 || !p.out_col_stride) return false;
+            ScatterMaps sm;                  // 4 KiB of tensor maps, copied into the launch as a __grid_constant__
+            memset(&sm, 0, sizeof sm);
+            u32 lc = 0;
+            while ((4096ull << lc) < N) lc++;
+            sm.log_chunks = lc;
+            const u64 dblk[4] = {16, N / 16, ncols, 1};
+            const u64 sblk[3] = {16, p.out_col_stride, p.out_col_stride};
+            const u64 sdup[3] = {16, p.dup_col_stride ? p.dup_col_stride : N, p.dup_col_stride ? p.dup_col_stride : N};
+            for (u32 q = 0; q < ncos; q++) {
+                if (!p.host_cos_ptr[q] || !make_map(&sm.out[q], p.host_cos_ptr[q], dblk, sblk)) return false;
+                if (p.host_dup_ptr && p.host_dup_ptr[q]) {
+                    if (!make_map(&sm.dup[q], p.host_dup_ptr[q], dblk, sdup)) return false;
+                    sm.dup_mask |= 1u << q;
+                }
+            }
+            const u64 din[4] = {16, words / 16, ncols, 1};
+            const u64 sin_[3] = {16, p.in_col_stride ? p.in_col_stride : words, p.in_col_stride ? p.in_col_stride : words};
+            if (!make_map(&mi, in, din, sin_)) return false;
+            return g_groups == 3 ? launch_scatter<3>(mi, sm, A, stream) : launch_scatter<2>(mi, sm, A, stream);
+        }
         const u64 d[4] = {16, words / 16, ncols, 1};
         const u64 s[3] = {16, p.in_col_stride ? p.in_col_stride : words, p.in_col_stride ? p.in_col_stride : words};
         if (!make_map(&mi, in, d, s) || !make_map(&mo, out, d, s)) return false;

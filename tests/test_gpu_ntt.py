@@ -256,7 +256,8 @@ def test_structured_columns_all_transforms(ctx, orc, log_n):
     assert np.array_equal(got, orc.ntt(q, 3, log_n, inverse=True))
 
 
-@pytest.mark.parametrize("log_n,log_b,ncols,field", [(10, 3, 5, 1), (13, 3, 3, 1), (16, 2, 4, 1), (5, 3, 2, 1), (12, 3, 2, 3), (4, 1, 3, 1)])
+@pytest.mark.parametrize("log_n,log_b,ncols,field", [(10, 3, 5, 1), (13, 3, 3, 1), (16, 2, 4, 1), (5, 3, 2, 1), (12, 3, 2, 3), (4, 1, 3, 1),
+                                                     (16, 3, 32, 1)])     # the last one is large enough for the TMA pipeline (scatter through per-block tensor maps)
 @pytest.mark.parametrize("world", [2, 4])
 def test_lde_scatter_into_row_slabs(ctx, orc, log_n, log_b, ncols, field, world):
     """ms_lde_batch_scatter (the multi-GPU fused exchange) with the "peer" slabs on the same device: every coset block
@@ -282,3 +283,98 @@ def test_lde_scatter_into_row_slabs(ctx, orc, log_n, log_b, ncols, field, world)
         assert np.array_equal(got[lo:lo + ncols], want[:, j * rows_per * field:(j + 1) * rows_per * field]), j
         assert not got[:lo].any() and not got[lo + ncols:].any()          # other ranks' columns untouched
     assert np.array_equal(work.cpu().numpy().view(np.uint64)[:, :n * field], want[:, :n * field])
+
+
+# ---- the persistent TMA pipeline (csrc/ntt_tma.cu) against the oracle and against the one-tile-per-CTA kernel --------------
+@pytest.mark.parametrize("log_b,ncols", [(3, 8), (2, 16), (0, 64), (4, 5)])
+def test_tma_pipeline_lde_2p16_vs_oracle(ctx, orc, log_b, ncols):
+    """2^16 points = digits [8, 8]: a strided pass (with the coset pre-scale tile) + the contiguous pass, both on the TMA
+    pipeline when it is switched on; bit-reversed LDE compared with the oracle word for word, and the two kernels with each other"""
+    torch = pytest.importorskip("torch")
+    log_n = 16
+    n = 1 << log_n
+    coeffs = orc.rand_matrix(ncols, n, 1, seed=300 + log_b)
+    coeffs[0, :10] = [0, 1, ms.P - 1, ms.P - 2, 2**32 - 1, 2**32, 2**32 + 1, 0xFFFFFFFF00000000, 2**63, ms.P - 2**32]
+    want = orc.lde(coeffs, 1, log_n, log_b, orc.generator(), bitrev=True)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        c2 = ms.Context(0, stream=stream.cuda_stream)
+        dev = torch.from_numpy(coeffs.view(np.int64)).cuda()
+        out = torch.empty((ncols, n << log_b), dtype=torch.int64, device="cuda")
+        got = {}
+        try:
+            for tma in (1, 0):
+                c2.set_option("ntt_tma", tma)
+                out.zero_()
+                c2.lde_batch(dev, out, ms.FP, log_n, log_b, ncols)
+                c2.sync()
+                got[tma] = out.cpu().numpy().view(np.uint64).copy()
+        finally:
+            c2.set_option("ntt_tma", 1)
+    assert np.array_equal(got[1], want)
+    assert np.array_equal(got[0], want)
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("coset", [False, True])
+def test_tma_pipeline_natural_order_ntt_2p16(ctx, orc, inverse, coset):
+    """natural-order transforms: the strided pass runs on the TMA pipeline with the natural digit placement (and the
+    inverse constants), the transposing last pass on the tile kernel"""
+    torch = pytest.importorskip("torch")
+    ncols, log_n = 64, 16
+    offset = orc.generator() if coset else orc.ONE
+    cols = orc.rand_matrix(ncols, 1 << log_n, 1, seed=5)
+    want = orc.ntt(cols, 1, log_n, offset, inverse=inverse)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        c2 = ms.Context(0, stream=stream.cuda_stream)
+        try:
+            for tma in (1, 0):
+                c2.set_option("ntt_tma", tma)
+                d = torch.from_numpy(cols.view(np.int64)).cuda()
+                c2.ntt_batch(d, ms.FP, log_n, ncols, inverse=inverse, offset=offset)
+                c2.sync()
+                assert np.array_equal(d.cpu().numpy().view(np.uint64), want)
+        finally:
+            c2.set_option("ntt_tma", 1)
+
+
+def test_tma_pipeline_2p24_equals_tile_kernel_and_groups(ctx):
+    """three passes at the config-3 transform size: TMA pipeline (2 and 3 consumer groups, a short stage ring) against the
+    one-tile-per-CTA kernel, bit for bit, for the LDE and for natural-order forward / inverse transforms"""
+    torch = pytest.importorskip("torch")
+    log_n, log_b, ncols = 24, 3, 2
+    n = 1 << log_n
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        c2 = ms.Context(0, stream=stream.cuda_stream)
+        a = torch.empty((ncols, n), dtype=torch.int64, device="cuda")
+        c2.fill_random(a, ncols * n, 11)
+        ref = torch.empty((ncols, n << log_b), dtype=torch.int64, device="cuda")
+        got = torch.empty_like(ref)
+        try:
+            c2.set_option("ntt_tma", 0)
+            c2.lde_batch(a, ref, ms.FP, log_n, log_b, ncols)
+            for groups, stages in ((2, 8), (3, 8), (2, 3)):
+                c2.set_option("ntt_tma", 1)
+                c2.set_option("ntt_tma_groups", groups)
+                c2.set_option("ntt_tma_stages", stages)
+                got.zero_()
+                c2.lde_batch(a, got, ms.FP, log_n, log_b, ncols)
+                c2.sync()
+                assert torch.equal(got, ref), (groups, stages)
+            c2.set_option("ntt_tma_groups", 2)
+            c2.set_option("ntt_tma_stages", 8)
+            for inverse in (True, False):
+                outs = {}
+                for tma in (0, 1):
+                    c2.set_option("ntt_tma", tma)
+                    d = a.clone()
+                    c2.ntt_batch(d, ms.FP, log_n, ncols, inverse=inverse, offset=ms.GENERATOR)
+                    c2.sync()
+                    outs[tma] = d
+                assert torch.equal(outs[0], outs[1])
+        finally:
+            c2.set_option("ntt_tma", 1)
+            c2.set_option("ntt_tma_groups", 2)
+            c2.set_option("ntt_tma_stages", 8)
