@@ -108,30 +108,32 @@ class _ShardedTree:
 
 class _FetchPlan:
     """The query phase needs ~30 LDE rows per matrix, ~30 rows per FRI layer and a few hundred path digests, each living
-    on the rank that owns its row.  Requests are collected first, every rank then fetches what it owns with one device
-    gather per matrix / tree, and ONE all-gather of the (small) pieces gives every rank everything."""
+    on the rank that owns its row.  Requests are collected first (every rank builds the same plan, so every rank knows
+    who owns what and how many bytes it is), every rank then fetches what it owns with one device gather per matrix /
+    tree, and ONE fixed-layout NCCL all-gather of the packed pieces gives every rank everything."""
 
     def __init__(self, prover):
         self.p = prover
-        self.groups = []          # (fetch(list of local indices) -> sequence of byte strings / arrays, [(item, local index)])
-        self.nitems = 0
+        self.groups = []          # (fetch(list of local indices) -> sequence of byte strings, [(item, local index)])
+        self.items = []           # per handle: (owner rank or None for a literal, nbytes)
         self.literal = {}
         self.data = None
 
-    def _new(self):
-        self.nitems += 1
-        return self.nitems - 1
+    def _new(self, owner, nbytes):
+        self.items.append((owner, nbytes))
+        return len(self.items) - 1
 
-    def rows(self, gather_local, n_local, positions):
-        """handles of the rows at global `positions`; gather_local(list of local row ids) -> (k, words) array"""
+    def rows(self, gather_local, n_local, positions, row_words):
+        """handles of the rows at global `positions`; gather_local(list of local row ids) -> (k, row_words) array"""
         mine, handles = [], []
         for p in positions:
-            h = self._new()
+            owner = p // n_local
+            h = self._new(owner, 8 * row_words)
             handles.append(h)
-            if p // n_local == self.p.rank:
-                mine.append((h, p - self.p.rank * n_local))
+            if owner == self.p.rank:
+                mine.append((h, p - owner * n_local))
         if mine:
-            self.groups.append((lambda loc, f=gather_local: [np.asarray(r, dtype=np.uint64).copy() for r in f(loc)], mine))
+            self.groups.append((lambda loc, f=gather_local: [np.ascontiguousarray(r, dtype=np.uint64).tobytes() for r in f(loc)], mine))
         return handles
 
     def view(self, tree, positions):
@@ -140,15 +142,15 @@ class _FetchPlan:
         leaf_mine, node_mine = [], []
 
         def leaf(i):
-            h = self._new()
             owner, loc = divmod(i, tree.n_local)
+            h = self._new(owner, 32)
             if owner == self.p.rank:
                 leaf_mine.append((h, loc))
             return h
 
         def node(k):
-            h = self._new()
             owner, loc = node_owner(k, self.p.log_g)
+            h = self._new(owner, 32)
             if owner is None:
                 self.literal[h] = tree.top[loc] if loc else bytes(32)     # heap index 0: the unused default digest
             elif owner == self.p.rank:
@@ -168,18 +170,36 @@ class _FetchPlan:
         return hp, hi, hs, tree.n_total.bit_length() - 1
 
     def execute(self):
-        mine = dict(self.literal) if self.p.rank == 0 else {}
+        G, rank = self.p.world, self.p.rank
+        mine = {}
         for fn, lst in self.groups:
             for (h, _), v in zip(lst, fn([loc for _, loc in lst])):
                 mine[h] = v
-        self.data = {}
-        for part in self.p._all_gather_objects(mine):
-            self.data.update(part)
-        self.data.update(self.literal)
-        assert len(self.data) == self.nitems, "a queried row or digest has no owner"
+        # fixed layout: rank r's buffer = its items in handle order; every rank can compute every offset
+        sizes = [0] * G
+        offset = {}
+        for h, (owner, nbytes) in enumerate(self.items):
+            if owner is not None:
+                offset[h] = sizes[owner]
+                sizes[owner] += nbytes
+        cap = max(max(sizes), 1)
+        buf = bytearray(cap)
+        for h, v in mine.items():
+            assert len(v) == self.items[h][1]
+            buf[offset[h]:offset[h] + len(v)] = v
+        send = torch.frombuffer(buf, dtype=torch.uint8).to(self.p.device)
+        recv = torch.empty(G * cap, dtype=torch.uint8, device=self.p.device)
+        self.p.dist.all_gather_into_tensor(recv, send)
+        raw = recv.cpu().numpy().tobytes()
+        self.data = dict(self.literal)
+        for h, (owner, nbytes) in enumerate(self.items):
+            if owner is not None:
+                o = owner * cap + offset[h]
+                self.data[h] = raw[o:o + nbytes]
+        assert len(self.data) == len(self.items), "a queried row or digest has no owner"
 
     def get_rows(self, handles):
-        return np.concatenate([self.data[h] for h in handles]) if handles else np.zeros(0, dtype=np.uint64)
+        return np.frombuffer(b"".join(self.data[h] for h in handles), dtype=np.uint64) if handles else np.zeros(0, dtype=np.uint64)
 
     def get_view(self, v):
         hp, hi, hs, height = v
@@ -503,7 +523,7 @@ class ShardedProver(GpuProver):
             folded = sorted(set(p // ff for p in folded))
             if was_sharded:
                 nloc = nrows // G
-                hr = plan.rows(lambda loc, e=evals, k=nloc: ctx.gather_rows_rowmajor(e, ff * fq, k, loc), nloc, folded)
+                hr = plan.rows(lambda loc, e=evals, k=nloc: ctx.gather_rows_rowmajor(e, ff * fq, k, loc), nloc, folded, ff * fq)
                 pending.append((root, hr, plan.view(tree, folded), None))
             else:
                 rows = ctx.gather_rows_rowmajor(evals, ff * fq, nrows, folded)
@@ -511,7 +531,8 @@ class ShardedProver(GpuProver):
 
         def trace_rows(slab, field, ncols):
             # Queries::new keeps the caller's position order (sorted, deduplicated by draw_queries)
-            return plan.rows(lambda loc: ctx.gather_rows(slab, field, rows_per, ncols, loc, col_stride=rows_per), rows_per, positions)
+            return plan.rows(lambda loc: ctx.gather_rows(slab, field, rows_per, ncols, loc, col_stride=rows_per), rows_per, positions,
+                             ncols * field)
 
         h_base, h_comp = trace_rows(base_slab, FP, nbase), trace_rows(comp_slab, fq, ce_blowup)
         h_ext = trace_rows(ext_slab, fq, next_) if next_ else None
