@@ -616,6 +616,27 @@ bool launch_pass_tma(const PassParams &p, const Tables &t, bool inverse, const u
         if (p.out_cos_ptr) {
             // scatter: chunks are read from the work buffer (in) and stored through per-block tensor maps
             if (ncos > (u32)kMaxScatterCos || N < 4096 || !p.out_col_stride) return false;
+            {
+                // TMA stores of whole 32 KiB tiles into PEER memory hold their ring stage until the link has taken the
+                // tile; measured on the config-3 step: with half of the blocks remote (2 GPUs) the TMA
+                // scatter wins (144.8 vs 147.2 ms), with 7/8 remote (8 GPUs) the one-tile-per-CTA kernel, whose many
+                // warps keep more stores in flight, does (157.6 vs 160.2 ms).  So: TMA scatter while at most half of the
+                // destination blocks live on another device.
+                int dev = 0;
+                cudaGetDevice(&dev);
+                u32 remote = 0;
+                for (u32 q = 0; q < ncos; q++) {
+                    cudaPointerAttributes at;
+                    if (cudaPointerGetAttributes(&at, p.host_cos_ptr[q]) != cudaSuccess) {
+                        cudaGetLastError();
+                        remote++;
+                    } else if (at.device != dev) {
+                        remote++;
+                    }
+                }
+                static const bool force = [] { const char *e = getenv("MS_NTT_TMA_SCATTER"); return e && e[0] == '1'; }();
+                if (2 * remote > ncos && !force) return false;
+            }
             ScatterMaps sm;                  // 4 KiB of tensor maps, copied into the launch as a __grid_constant__
             memset(&sm, 0, sizeof sm);
             u32 lc = 0;
