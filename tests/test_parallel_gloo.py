@@ -90,6 +90,12 @@ class PeerOracleEngine(OracleEngine):
     def rendezvous(self, dist):
         dist.barrier()              # the CPU engine is synchronous: a host barrier is the whole rendezvous
 
+    def ipc_close(self, ptr):
+        self.closed = getattr(self, "closed", 0) + 1
+
+    def free_exportable(self, ptr):
+        self.freed = True
+
     def _store(self, addr, words):
         local = bool(addr & self.LOCAL)
         addr &= self.LOCAL - 1
@@ -142,7 +148,8 @@ def _worker(rank, world, port, log_n, log_b, ncols, q, fused=False):
             n = 1 << log_n                           # the local copy of block 0 (ce-domain prefix)
             want = orc.lde(orc.ntt(full[lo:hi], 1, log_n, inverse=True), 1, log_n, log_b, orc.generator(), True)
             assert np.array_equal(sc.lde.numpy().view(np.uint64)[:, :n], want[:, :n])
-            dist.barrier()
+            sc.close()                               # unmaps the peers' slabs, frees its own, falls back to unfused state
+            assert not sc.fused and eng.closed == world - 1 and eng.freed
             eng.close()
         q.put((rank, root))
     finally:

@@ -48,18 +48,26 @@ impl AirConfig for FibAir {
         let first = Constant(FieldVariant::Fp(xs.element(0)));
         let last = Constant(FieldVariant::Fp(xs.element(trace_len - 1)));
         let one = Constant(FieldVariant::Fp(Fp::one()));
-        // the first row holds v_0 .. v_7
-        let mut v = vec![one, one + one];
-        for i in 2..8 {
-            let next = &v[i - 2] * &v[i - 1];
-            v.push(next);
-        }
-        let mut cs = Vec::new();
-        for (i, vi) in v.into_iter().enumerate() {
-            cs.push((i.curr() - vi) / (X - first));
-        }
+        // the first row holds v_0 .. v_7 (written out like the example: a sum of two items is an Expr, products take refs)
+        let v0 = one;
+        let v1 = v0 + v0;
+        let v2 = &v1 * v0;
+        let v3 = &v1 * &v2;
+        let v4 = &v2 * &v3;
+        let v5 = &v3 * &v4;
+        let v6 = &v4 * &v5;
+        let v7 = &v5 * &v6;
+        let mut cs = vec![
+            (0.curr() - v0) / (X - first),
+            (1.curr() - v1) / (X - first),
+            (2.curr() - v2) / (X - first),
+            (3.curr() - v3) / (X - first),
+            (4.curr() - v4) / (X - first),
+            (5.curr() - v5) / (X - first),
+            (6.curr() - v6) / (X - first),
+            (7.curr() - v7) / (X - first),
+        ];
         cs.push((7.curr() - Hint(0)) / (X - last));
-        let all_rows_but_last = (X - last) / (X.pow(trace_len) - one);
         let step = vec![
             0.next() - 6.curr() * 7.curr(),
             1.next() - 7.curr() * 0.next(),
@@ -71,7 +79,8 @@ impl AirConfig for FibAir {
             7.next() - 5.next() * 6.next(),
         ];
         for c in step {
-            cs.push(c * &all_rows_but_last);
+            // every row but the last: (x - t_(n-1)) / (x^n - 1)
+            cs.push(c * ((X - last) / (X.pow(trace_len) - one)));
         }
         cs.into_iter().map(Constraint::new).collect()
     }
