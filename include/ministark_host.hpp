@@ -415,7 +415,7 @@ inline u64 blowup_factor(const Graph &g, int root, u64 trace_len) {
 }
 
 // ------------------------------------------------------------------------------------------------ evaluator programs
-enum Op : u32 { OP_X = 0, OP_CONST, OP_TRACE, OP_NEG, OP_ADD, OP_SUB, OP_MUL, OP_INV, OP_POW, OP_STORE };
+enum Op : u32 { OP_X = 0, OP_CONST, OP_TRACE, OP_NEG, OP_ADD, OP_SUB, OP_MUL, OP_INV, OP_POW, OP_STORE, OP_PERIODIC };   // csrc/eval.cu (OP_PERIODIC: periodic columns, emitted by the Python compiler only)
 constexpr int MAX_REGS = 48;
 struct Binding { u32 slot; Kind kind; u64 index; };
 struct Program {
