@@ -729,7 +729,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="resident steps only (for ncu captures)")
     ap.add_argument("--no-prover", action="store_true", help="skip the examples/fib full-prove sample")
     ap.add_argument("--prove-log-rows", type=int, default=22, help="rows of the config-5 (sharded) full-prove sample")
-    ap.add_argument("--cpu-prove-log-rows", type=int, default=18, help="--impl reference: rows of the CPU full-prove sample")
+    ap.add_argument("--cpu-prove-log-rows", type=int, default=21, help="--impl reference: rows of the CPU full-prove sample")
     ap.add_argument("--no-fused-exchange", action="store_true", help="N > 1: LDE then NCCL all-to-all instead of the fused scatter")
     ap.add_argument("--no-verify", action="store_true", help="skip the comparison with the committed oracle fixtures")
     ap.add_argument("--no-extra", action="store_true", help="skip the strong-scaling, FRI-sweep and sharded-prover arms")
