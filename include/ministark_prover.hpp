@@ -245,6 +245,7 @@ public:
         unsigned ln = log_N;
         for (unsigned l = 0; l < options.fri_num_layers(N); l++) {
             Layer L;
+            if (ln < log_ff) throw std::runtime_error("FRI: the evaluation domain is smaller than the folding factor");
             L.nrows = (u64)1 << (ln - log_ff);
             L.leaves = DeviceBuf(ctx, L.nrows * 32);
             L.nodes = DeviceBuf(ctx, L.nrows * 32);

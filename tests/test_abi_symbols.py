@@ -35,13 +35,13 @@ def test_product_never_imports_the_oracle():
     """the product may mention the oracle in prose; it must never import, load or link it"""
     import re
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    bad = re.compile(r"^\s*(from|import)\s+(\.+)?oracle\b|liboracle|gl_oracle|eval_oracle|synth_oracle|pyspec", re.M)
+    bad = re.compile(r"^\s*(from|import)\s+(\.+)?oracle\b|liboracle|gl_oracle|eval_oracle|synth_oracle|pyspec|cpu_abi|cpu_prover", re.M)
     for dirpath, _, files in os.walk(os.path.join(root, "ministark_b200")):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", "Makefile")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(text), f"{f} references the oracle"
-    for f in ("include/ministark_b200.h", "include/ministark_gpu.hpp"):
+    for f in ("include/ministark_b200.h", "include/ministark_gpu.hpp", "include/ministark_prover.hpp", "include/ministark_host.hpp"):
         assert not bad.search(open(os.path.join(root, f)).read())
 
 
