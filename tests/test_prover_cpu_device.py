@@ -90,7 +90,7 @@ def _sharded_worker(rank, world, port, which, q):
 
 
 @pytest.mark.parametrize("world,which", [(2, "fib:7:16,4,4,8,16"), (2, "fib:10:32,4,8,8,64"), (2, "perm"), (2, "brainfuck"),
-                                         (4, "fib:9:32,4,8,8,64"), (4, "brainfuck"), (2, "fib:6:10,2,0,2,8")])
+                                         (4, "fib:9:32,4,8,8,64"), (4, "brainfuck"), (2, "fib:6:10,2,0,2,8"), (8, "fib:8:16,8,3,4,8")])
 def test_sharded_prover_over_gloo_bytes_equal_cpu_restatement(orc, world, which):
     import torch.multiprocessing as mp
     s = socket.socket()
@@ -109,6 +109,70 @@ def test_sharded_prover_over_gloo_bytes_equal_cpu_restatement(orc, world, which)
     want = _cpu_restatement(which)
     for rank, first, second in got:                 # every rank assembles the same proof, twice
         assert first == second == want, f"rank {rank}"
+
+
+def _bad_input_worker(q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cpu_device
+    cpu_device.install()
+    import numpy as np
+    from ministark_b200.air import ProofOptions
+    from ministark_b200.examples import fib
+    from ministark_b200.prover import GpuProver, ProvingError
+    trace, last = fib.gen_trace(8 << 6)
+    cols = trace.base_columns().copy()
+    cols[3, 17] ^= np.uint64(1)
+    claim = fib.FibClaim(last)
+
+    class Witness:
+        def __init__(self, c):
+            self.c = c
+
+        def __len__(self):
+            return self.c.shape[1]
+
+        def base_columns(self):
+            return self.c
+
+        def build_extension_columns(self, challenges):
+            return None
+
+    p = GpuProver(0)
+    bad = p.prove(claim, ProofOptions(10, 4, 0, 8, 4), Witness(cols)).to_bytes()
+    try:
+        p.prove(claim, ProofOptions(10, 4, 0, 8, 4), Witness(cols[:7]))
+        shape_error = None
+    except ProvingError as e:
+        shape_error = str(e)
+    q.put((bad, shape_error))
+
+
+def test_python_prover_on_bad_inputs(orc):
+    """the prover never checks the AIR (src/debug.rs is debug-only): a trace that violates it still yields a proof — the
+    same bytes as the restated reference prover's — which the verifier refuses at the OOD consistency check
+    (src/verifier.rs:84-86); a trace of the wrong shape is an error before any device work"""
+    import numpy as np
+    import torch.multiprocessing as mp
+    from ministark_b200.air import Air, ProofOptions
+    from ministark_b200.examples import fib
+    from oracle import stark_oracle as SO
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_bad_input_worker, args=(q,))
+    p.start()
+    bad, shape_error = q.get(timeout=600)
+    p.join(timeout=60)
+    assert p.exitcode == 0
+    trace, last = fib.gen_trace(8 << 6)
+    cols = trace.base_columns().copy()
+    cols[3, 17] ^= np.uint64(1)
+    claim = fib.FibClaim(last)
+    mk = lambda n, o: Air(claim.AirConfig, n, claim.get_public_inputs(), ProofOptions(*o))
+    assert bad == SO.cpu_prove(claim, (10, 4, 0, 8, 4), cols, mk)
+    with pytest.raises(SO.VerificationError, match="out-of-domain"):
+        SO.verify(claim, bad, 10, mk)
+    assert shape_error and "expected 8 base columns" in shape_error
 
 
 def test_harness_is_not_reachable_from_the_product():
