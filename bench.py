@@ -259,11 +259,33 @@ def cpu_full_prove_compiled(log_rows):
             "seconds": r["seconds"], "proof_bytes": r["proof_bytes"], "verified": r["verified"], "cores": r["threads"], "kind": "port"}
 
 
+def cpu_brainfuck_prove_compiled(burner):
+    """examples/brainfuck, program cycle_burner(a, b, c) (40,40,60: 2^20 rows — the size of the GPU figure in
+    profiles/bench_brainfuck_burner_*.json), ProofOptions(19, 16, 20, 16, 16), through the same compiled CPU prover"""
+    from ministark_b200.examples import brainfuck as bf
+    odir = os.path.join(ROOT, "oracle")
+    try:
+        a, b, c = (int(v) for v in burner.split(","))
+        ii, mi = bf.test_rng_fq3(2)
+        subprocess.check_call(["make", "-s", "-C", odir, "cpu_prover"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        out = subprocess.run([os.path.join(odir, "cpu_prover"), "bf", str(a), str(b), str(c), "19", "16", "20", "16", "16"] + [str(v) for v in ii + mi],
+                             capture_output=True, text=True, timeout=3600)
+        if out.returncode != 0:
+            return {"unavailable": out.stderr.strip()[-200:]}
+        r = json.loads(out.stdout)
+    except Exception as e:
+        return {"unavailable": repr(e)[:200]}
+    return {"workload": f"examples/brainfuck: cycle_burner({a},{b},{c}), {r['rows']} rows x (17 Fp + 9 Fq3) columns, ProofOptions(19, 16, 20, 16, 16), "
+                        "C++ default_prove on the CPU build of the C ABI (VM run excluded)",
+            "seconds": r["seconds"], "proof_bytes": r["proof_bytes"], "verified": r["verified"], "cores": r["threads"], "kind": "port"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     log_n = args.cpu_log_n
+    no_prover = args.no_prover or args.gpus > 1
     t0 = time.perf_counter()
     for _ in range(args.warmup and 1):
         cpu_sample(log_n, args.ncols, LOG_BLOWUP)
@@ -287,8 +309,10 @@ def run_reference(args):
         "timed_sample": {"rows_log2": log_n, "of_rows_log2": args.log_n,
                          "note": "the CPU arm times this bounded sample of the workload; the metric is throughput, normalised by the "
                                  "field operations of the sample"},
-        "full_prove": None if args.no_prover else cpu_full_prove_sample(args.cpu_prove_log_rows),
-        "full_prove_compiled": None if args.no_prover else cpu_full_prove_compiled(args.cpu_prove_log_rows),
+        # CPU proves of the GPU arm's full-prove workloads (N-independent: reported with the N = 1 line only)
+        "full_prove": None if no_prover else cpu_full_prove_sample(args.cpu_prove_log_rows),
+        "full_prove_compiled": None if no_prover else cpu_full_prove_compiled(args.cpu_prove_log_rows),
+        "brainfuck_prove_compiled": None if no_prover or not args.cpu_bf_burner else cpu_brainfuck_prove_compiled(args.cpu_bf_burner),
         "wall_s": time.perf_counter() - t0,
     }))
 
@@ -749,6 +773,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="resident steps only (for ncu captures)")
     ap.add_argument("--no-prover", action="store_true", help="skip the examples/fib full-prove sample")
     ap.add_argument("--prove-log-rows", type=int, default=22, help="rows of the config-5 (sharded) full-prove sample")
+    ap.add_argument("--cpu-bf-burner", default="40,40,60", help="--impl reference: cycle_burner(a,b,c) of the compiled CPU brainfuck prove "
+                    "(40,40,60 = 2^20 rows; empty string: skip)")
     ap.add_argument("--cpu-prove-log-rows", type=int, default=21, help="--impl reference: rows of the CPU full-prove sample")
     ap.add_argument("--no-fused-exchange", action="store_true", help="N > 1: LDE then NCCL all-to-all instead of the fused scatter")
     ap.add_argument("--no-verify", action="store_true", help="skip the comparison with the committed oracle fixtures")
