@@ -83,6 +83,31 @@ def test_cpp_prover_brainfuck_bytes_equal_cpu_restatement(prover_exe, orc, which
     assert bytes.fromhex(hexbytes) == want
 
 
+def test_bench_baseline_binary(cpu_abi, orc):
+    """oracle/cpu_prover — what `bench.py --impl reference` times as the compiled CPU prove — emits the same bytes"""
+    import json
+    from oracle import stark_oracle as SO
+    from ministark_b200.examples import brainfuck as bf
+    subprocess.check_call(["make", "-s", "-C", ORACLE, "cpu_prover"])
+    exe = os.path.join(ORACLE, "cpu_prover")
+    opts = (32, 4, 8, 8, 64)
+    r = json.loads(subprocess.run([exe, "8"] + [str(o) for o in opts] + ["--hex"], capture_output=True, text=True, check=True).stdout)
+    trace, last = fib.gen_trace(8 << 8)
+    claim = fib.FibClaim(last)
+    mk = lambda n, o: Air(claim.AirConfig, n, claim.get_public_inputs(), ProofOptions(*o))
+    assert r["verified"] and r["rows"] == 256 and bytes.fromhex(r["proof_hex"]) == SO.cpu_prove(claim, opts, trace.base_columns(), mk)
+    ii, mi = bf.test_rng_fq3(2)
+    opts = (16, 16, 6, 8, 8)
+    r = json.loads(subprocess.run([exe, "bf", "4", "4", "4"] + [str(o) for o in opts] + [str(v) for v in ii + mi] + ["--hex"], capture_output=True,
+                                  text=True, check=True).stdout)
+    src = bf.cycle_burner(4, 4, 4)
+    trace, output = bf.simulate(src)
+    claim = bf.BrainfuckClaim(src, b"", output)
+    mk = lambda n, o: Air(claim.AirConfig, n, claim, ProofOptions(*o))
+    assert r["rows"] == 1024 and bytes.fromhex(r["proof_hex"]) == SO.cpu_prove(claim, opts, trace.base_columns(), mk,
+                                                                                ext_builder=trace.build_extension_columns)
+
+
 def test_cpp_prover_reports_library_errors(prover_exe):
     """the reference panics (gpu/src/stage.rs:55-75); the C++ layer turns a non-zero status into an exception carrying
     ms_last_error(): a 1-row FRI layer cannot be committed (merkle.rs:113-128 needs >= 2 leaves), and options whose
