@@ -168,9 +168,12 @@ static inline size_t bitrev(size_t i, unsigned log_n) {
     x = __builtin_bswap64(x);
     return (size_t)(x >> (64 - log_n));
 }
-/* gpu/src/utils.rs:4-11,32-42.  elem_words = 1 (Fp) or 3 (Fq3). */
+/* gpu/src/utils.rs:4-11,32-78.  elem_words = 1 (Fp) or 3 (Fq3).  Like the reference's parallel build: split over the
+ * threads from 2^17 elements up (every pair is swapped by its smaller index, so the iterations are independent);
+ * inside an enclosing parallel region (one column per thread) the loop stays serial. */
 void orc_bit_reverse(u64 *v, unsigned elem_words, unsigned log_n) {
     size_t n = (size_t)1 << log_n;
+    #pragma omp parallel for if (log_n >= 17) schedule(static)
     for (size_t i = 0; i < n; i++) {
         size_t j = bitrev(i, log_n);
         if (j > i)
@@ -277,9 +280,28 @@ static void distribute_powers(u64 *a, unsigned lanes, size_t n, u64 g, u64 c, in
     }
 }
 
+/* Work split of a batch of independent columns (the reference: one rayon task per column, src/matrix.rs:118-139, with
+ * ark-poly's own parallel FFT inside a task).  Whole columns per thread, unless that would leave half of the threads or
+ * more without a column: then the columns run one after the other with every butterfly level split over all threads
+ * (measured on 8 threads, 2^20 -> 2^23 LDE: 2 columns 0.92 s instead of 2.28 s, 4 columns 1.83 s instead of 2.58 s; from
+ * 8 columns up whole columns win).  So 32 columns on 32 threads (config 3) or 17 on 8 run by columns; the 8 columns of
+ * examples/fib on a 32-thread host run level-parallel.  ORACLE_COLUMN_PARALLEL=0|1 forces one or the other (A/B). */
+static int column_parallel(unsigned ncols) {
+#ifdef _OPENMP
+    const unsigned t = (unsigned)omp_get_max_threads();
+#else
+    const unsigned t = 1;
+#endif
+    const char *e = getenv("ORACLE_COLUMN_PARALLEL");
+    if (ncols <= 1 || t <= 1) return 0;
+    if (e && *e) return *e != '0';
+    return 2 * ncols > t;
+}
+
 static void ntt_column(u64 *a, unsigned lanes, unsigned log_n, u64 offset, int inverse,
                        const u64 *roots, int par) {
     size_t n = (size_t)1 << log_n;
+    if (log_n < 12) par = 0;   /* a few thousand butterflies: forking a team per level costs more than the level */
     if (!inverse) {
         /* in_order_fft_in_place: distribute offset powers, DIF, derange */
         if (offset != GL_ONE) distribute_powers(a, lanes, n, offset, GL_ONE, par);
@@ -304,7 +326,7 @@ void orc_ntt_columns(u64 *base, size_t col_stride_words, unsigned ncols, unsigne
     u64 root = orc_root_of_unity(log_n);
     if (inverse) root = fp_inv(root);
     u64 *roots = roots_table(root, n >> 1);
-    int par_cols = ncols > 1;
+    int par_cols = column_parallel(ncols);
     #pragma omp parallel for if (par_cols) schedule(dynamic, 1)
     for (unsigned c = 0; c < ncols; c++)
         ntt_column(base + (size_t)c * col_stride_words, lanes, log_n, offset_mont, inverse, roots, !par_cols);
@@ -324,7 +346,8 @@ void orc_lde_columns(const u64 *in_base, size_t in_stride_words, u64 *out_base, 
     size_t n = (size_t)1 << log_n, N = (size_t)1 << log_N, dup = (size_t)1 << log_blowup;
     u64 root = orc_root_of_unity(log_N);
     u64 *roots = roots_table(root, N >> 1);
-    int par_cols = ncols > 1;
+    int par_cols = column_parallel(ncols);
+    const int par_in = !par_cols && log_N >= 12;
     #pragma omp parallel for if (par_cols) schedule(dynamic, 1)
     for (unsigned c = 0; c < ncols; c++) {
         const u64 *in = in_base + (size_t)c * in_stride_words;
@@ -332,19 +355,20 @@ void orc_lde_columns(const u64 *in_base, size_t in_stride_words, u64 *out_base, 
         if (log_blowup >= 2) {
             u64 *tmp = (u64 *)malloc(sizeof(u64) * n * lanes);
             memcpy(tmp, in, sizeof(u64) * n * lanes);
-            if (offset_mont != GL_ONE) distribute_powers(tmp, lanes, n, offset_mont, GL_ONE, !par_cols);
+            if (offset_mont != GL_ONE) distribute_powers(tmp, lanes, n, offset_mont, GL_ONE, par_in);
+            #pragma omp parallel for if (par_in) schedule(static)
             for (size_t i = 0; i < n; i++) {
                 size_t ri = bitrev(i, log_N); /* multiple of dup */
                 for (size_t d = 0; d < dup; d++)
                     for (unsigned l = 0; l < lanes; l++) out[(ri + d) * lanes + l] = tmp[i * lanes + l];
             }
             free(tmp);
-            dit_levels(out, lanes, log_N, roots, dup, !par_cols);
+            dit_levels(out, lanes, log_N, roots, dup, par_in);
         } else {
             memset(out, 0, sizeof(u64) * N * lanes);
             memcpy(out, in, sizeof(u64) * n * lanes);
-            if (offset_mont != GL_ONE) distribute_powers(out, lanes, n, offset_mont, GL_ONE, !par_cols);
-            dif_levels(out, lanes, log_N, roots, !par_cols);
+            if (offset_mont != GL_ONE) distribute_powers(out, lanes, n, offset_mont, GL_ONE, par_in);
+            dif_levels(out, lanes, log_N, roots, par_in);
             orc_bit_reverse(out, lanes, log_N);
         }
         if (bitrev_out) orc_bit_reverse(out, lanes, log_N);
