@@ -678,6 +678,24 @@ void orc_divide_out_points(u64 *coeffs, size_t n, const u64 *zs, const u64 *cs, 
         for (unsigned j = 0; j < k; j++) rem[j] = fq3_add(fq3_mul(load_el(zs, 3, j), rem[j]), tmp);
     }
 }
+/* get_ood_evals (src/composer.rs:60-83): one Horner evaluation per (column, point) job, jobs across the threads like the
+ * reference's cfg_into_iter over the trace arguments */
+void orc_horner_jobs(const u64 *const *coeffs, const unsigned *cf, size_t n, const u64 *points, unsigned njobs, u64 *out) {
+    #pragma omp parallel for schedule(dynamic, 1)
+    for (unsigned j = 0; j < njobs; j++) orc_horner(coeffs[j], cf[j], n, points + 3 * (size_t)j, out + 3 * (size_t)j);
+}
+/* into_deep_poly (src/composer.rs:108-158): every column divided by its own points, columns across the threads.
+ * cols: ncols columns of n Fq3 coefficients (in place); column c uses counts[c] points from the running lists zs / cs */
+void orc_divide_out_points_columns(u64 *base, size_t col_stride_words, unsigned ncols, size_t n, const u64 *zs, const u64 *cs,
+                                   const unsigned *counts) {
+    size_t *start = (size_t *)malloc(sizeof(size_t) * (ncols + 1));
+    start[0] = 0;
+    for (unsigned c = 0; c < ncols; c++) start[c + 1] = start[c] + counts[c];
+    #pragma omp parallel for schedule(dynamic, 1)
+    for (unsigned c = 0; c < ncols; c++)
+        orc_divide_out_points(base + (size_t)c * col_stride_words, n, zs + 3 * start[c], cs + 3 * start[c], counts[c]);
+    free(start);
+}
 /* running product / running evaluation columns as the reference builds them row by row
  * (examples/brainfuck/trace.rs:108-279):  x_0 = init, x_(i+1) = x_i * a_i + b_i;
  * out[i] = x_i (exclusive: the value stored BEFORE the row's update) or x_(i+1) (inclusive).

@@ -230,6 +230,40 @@ def divide_out_points(coeffs, zs, cs):
     return out
 
 
+def horner_jobs(jobs):
+    """jobs: [(coeffs array, coefficient lanes, point as 3 Montgomery words)], all of the same length; evaluated across the
+    host threads (get_ood_evals, src/composer.rs:60-83).  Returns (njobs, 3) Montgomery words."""
+    k = len(jobs)
+    out = np.empty((k, 3), dtype=np.uint64)
+    if not k:
+        return out
+    arrs = [np.ascontiguousarray(j[0]) for j in jobs]
+    n = arrs[0].size // jobs[0][1]
+    assert all(a.size // j[1] == n for a, j in zip(arrs, jobs))
+    ptrs = (C.c_void_p * k)(*[a.ctypes.data for a in arrs])
+    cf = (C.c_uint * k)(*[j[1] for j in jobs])
+    pts = np.ascontiguousarray(np.concatenate([np.asarray(j[2], dtype=np.uint64).reshape(3) for j in jobs]))
+    f = lib().orc_horner_jobs
+    f.restype, f.argtypes = None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint, C.c_void_p]
+    f(ptrs, cf, n, pts.ctypes.data, k, out.ctypes.data)
+    return out
+
+
+def divide_out_points_columns(cols, zs_per_col, cs_per_col):
+    """cols: (ncols, 3n) Fq3 coefficient columns, divided IN PLACE, each by its own list of points (Montgomery word
+    triples) with its own coefficients, columns across the host threads (into_deep_poly, src/composer.rs:108-158)"""
+    assert cols.dtype == np.uint64 and cols.flags["C_CONTIGUOUS"]
+    ncols = cols.shape[0]
+    counts = (C.c_uint * max(ncols, 1))(*[np.asarray(z).size // 3 for z in zs_per_col])
+    flat = lambda per: np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.uint64).reshape(-1) for v in per] or [np.zeros(0, np.uint64)]))
+    zs, cs = flat(zs_per_col), flat(cs_per_col)
+    assert zs.size == cs.size == 3 * sum(counts) and len(zs_per_col) == len(cs_per_col) == ncols
+    f = lib().orc_divide_out_points_columns
+    f.restype, f.argtypes = None, [C.c_void_p, C.c_size_t, C.c_uint, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    f(cols.ctypes.data, cols.shape[1], ncols, cols.shape[1] // 3, zs.ctypes.data, cs.ctypes.data, counts)
+    return cols
+
+
 def degree_adjust(coeffs, alpha, beta):
     out = np.ascontiguousarray(coeffs).copy()
     lib().orc_degree_adjust(_p(out), out.size // 3, _p(np.ascontiguousarray(alpha, dtype=np.uint64)),

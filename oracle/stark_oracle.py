@@ -574,12 +574,12 @@ def cpu_prove(stark, options5, base_trace, make_air, ext_builder=None, timings=N
     def col_poly(col):
         return (base_polys[col], 1) if col < nbase else (ext_polys[col - nbase], lanes)
 
-    trace_oods = []
-    for col, off in trace_args:
-        cp, cl = col_poly(col)
-        trace_oods.append(_canon(orc.horner(cp, cl, _mont_vec([zpt(off)], 3)), 3)[0])
+    # one Horner evaluation per trace argument / composition column, spread over the threads as the reference's
+    # cfg_into_iter does (composer.rs:60-83)
     z_n = q_pow(z, ce_blowup)
-    comp_oods = [_canon(orc.horner(comp_polys[j], lanes, _mont_vec([z_n], 3)), 3)[0] for j in range(ce_blowup)]
+    oods = _canon(orc.horner_jobs([col_poly(col) + (_mont_vec([zpt(off)], 3),) for col, off in trace_args] +
+                                  [(comp_polys[j], lanes, _mont_vec([z_n], 3)) for j in range(ce_blowup)]).reshape(-1), 3)
+    trace_oods, comp_oods = oods[:len(trace_args)], oods[len(trace_args):]
     if lanes == 1 and any(v[1] or v[2] for v in trace_oods + comp_oods):
         raise AssertionError("ood value left the base field")
     coin.reseed_elements(trace_oods + comp_oods)
@@ -594,13 +594,21 @@ def cpu_prove(stark, options5, base_trace, make_air, ext_builder=None, timings=N
         out[0::3] = col
         return out
 
-    quotients = [orc.divide_out_points(lift_col(comp_polys[j], lanes), _mont_vec([z_n], 3), _mont_vec([co_alphas[j]], 3))
-                 for j in range(ce_blowup)]
+    # every column lifted to Fq3 and divided by its own points, columns across the threads (composer.rs:108-158)
+    quotients = np.empty((ce_blowup + nbase + next_, 3 * n), dtype=np.uint64)
+    zs, cs = [], []
+    for j in range(ce_blowup):
+        quotients[j] = lift_col(comp_polys[j], lanes)
+        zs.append(_mont_vec([z_n], 3))
+        cs.append(_mont_vec([co_alphas[j]], 3))
     for col in range(nbase + next_):
         sel = [(zpt(off), a) for (c, off), a in zip(trace_args, ex_alphas) if c == col]
         cp, cl = col_poly(col)
-        quotients.append(orc.divide_out_points(lift_col(cp, cl), _mont_vec([s[0] for s in sel], 3), _mont_vec([s[1] for s in sel], 3)))
-    deep_poly = orc.degree_adjust(orc.sum_columns(np.stack(quotients), 3), _mont_vec([d_alpha], 3), _mont_vec([d_beta], 3))
+        quotients[ce_blowup + col] = lift_col(cp, cl)
+        zs.append(_mont_vec([s[0] for s in sel], 3))
+        cs.append(_mont_vec([s[1] for s in sel], 3))
+    orc.divide_out_points_columns(quotients, zs, cs)
+    deep_poly = orc.degree_adjust(orc.sum_columns(quotients, 3), _mont_vec([d_alpha], 3), _mont_vec([d_beta], 3))
     if lanes == 1:
         assert not deep_poly[1::3].any() and not deep_poly[2::3].any()
         deep_poly = np.ascontiguousarray(deep_poly[0::3])
