@@ -245,3 +245,32 @@ def test_scan_affine_oracle_vs_definition(orc):
     canon = lambda arr: [tuple(S.from_mont(int(w)) for w in arr[3 * i:3 * i + 3]) for i in range(n)]
     assert canon(orc.scan_affine(3, n, init, a=a, fa=3, b=b, fb=1, inclusive=False)) == want_ex
     assert canon(orc.scan_affine(3, n, init, a=a, fa=3, b=b, fb=1, inclusive=True)) == want_in
+
+
+def test_work_split_does_not_change_results(orc):
+    """the oracle's two ways of using the threads (whole columns per thread / every butterfly level across the threads) and
+    the parallel bit reverse (from 2^17 elements, gpu/src/utils.rs:48-78) give the same words, whatever the thread count"""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import hashlib, numpy as np
+from oracle import oracle as orc
+h = hashlib.sha256()
+for lanes, ncols in ((1, 3), (3, 2)):
+    m = orc.rand_matrix(ncols, 1 << 15, lanes, seed=ncols)
+    p = orc.ntt(m, lanes, 15, inverse=True)
+    assert np.array_equal(orc.ntt(p, lanes, 15), m)
+    h.update(p.tobytes())
+    h.update(orc.lde(p, lanes, 15, 2, orc.generator(), True).tobytes())       # 2^17 points: the parallel bit reverse
+    h.update(orc.lde(p, lanes, 15, 1, orc.generator(), False).tobytes())      # the zero-padded DIF branch
+print(h.hexdigest())
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    got = set()
+    for env in ({"ORACLE_COLUMN_PARALLEL": "1"}, {"ORACLE_COLUMN_PARALLEL": "0"}, {"OMP_NUM_THREADS": "1"}, {"OMP_NUM_THREADS": "5"}):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, cwd=root)
+        assert out.returncode == 0, out.stderr
+        got.add(out.stdout.strip())
+    assert len(got) == 1
