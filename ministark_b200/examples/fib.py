@@ -55,11 +55,14 @@ class FibAirConfig(AirConfig):
         return boundary + terminal + transition
 
 
-def gen_trace(n, pinned=False):
+def gen_trace(n, pinned=False, device=None):
     """n = total number of sequence values; the trace has n / 8 rows of 8 consecutive values (main.rs:175-222).
     v_0 = 1, v_1 = 2, v_k = v_(k-2) * v_(k-1).  Returns (Trace, last value of column 7 as a canonical int).
     pinned: put the columns in page-locked host memory (the reference allocates them with GpuAllocator, main.rs:181-188)
-    so that the prover's chunked upload overlaps with the transforms."""
+    so that the prover's chunked upload overlaps with the transforms.
+    device: build the columns ON that device (SURVEY.md §8f rank 3 for this example): only the period of the sequence —
+    a few rows, see below — is computed on the host and uploaded, the (8, n/8) matrix is tiled from it in device memory
+    and handed to the prover as a resident tensor; nothing of size n crosses PCIe."""
     assert n & (n - 1) == 0 and n > 8
     num_rows = n // 8
     # v_k = 2^F(k) and 2 has order 192 in Goldilocks, so the sequence is periodic (period 96 = Pisano(192));
@@ -78,8 +81,15 @@ def gen_trace(n, pinned=False):
         v = nv
     period = np.array([[x * 2**64 % P for x in r] for r in rows], dtype=np.uint64)          # Montgomery words
     reps = -(-num_rows // len(rows))
-    cols = np.ascontiguousarray(np.tile(period, (reps, 1))[:num_rows].T)
     last = rows[(num_rows - 1) % len(rows)][7]
+    if device is not None:
+        import torch
+        block = torch.from_numpy(period.view(np.int64)).to(device)                             # (period rows, 8)
+        cols = block.repeat(reps, 1)[:num_rows].t().contiguous()
+        if cols.is_cuda:        # the prover reads the tensor on its own stream: hand it over complete
+            torch.cuda.current_stream(cols.device).synchronize()
+        return Trace(cols), last
+    cols = np.ascontiguousarray(np.tile(period, (reps, 1))[:num_rows].T)
     if pinned:
         import torch
         host = torch.empty((8, num_rows), dtype=torch.int64, pin_memory=True)
