@@ -38,11 +38,14 @@ inline void ck(ms_ctx *c, int rc, const char *what) {
     if (rc != MS_OK) throw std::runtime_error(std::string(what) + ": " + ms_last_error(c));   // the reference panics
 }
 
-// DEEP composition as a symbolic expression over LDE columns [base..., composition...] (ministark_b200/deep.py):
-// hints are, in order of first use: composition ood / z^m / composition alpha per column, then per trace argument
-// its ood value, its point z*g^offset (shared per offset) and its alpha, then the two degree coefficients.
+// DEEP composition as a symbolic expression over LDE columns [base..., composition...] (ministark_b200/deep.py), with the
+// terms grouped by their out-of-domain point:
+//     sum_j a_j (P_j(x) - P_j(z_k)) / (x - z_k)  =  (sum_j a_j P_j(x) - K_k) / (x - z_k),      K_k = sum_j a_j P_j(z_k)
+// one multiplication by a_j per column and one Fq x Fq product per distinct point (z^m and z*g^o per trace offset o).
+// Hints, in order of first use: per group the alphas of its columns, the constant K_k and the point; then the two
+// degree coefficients.
 struct DeepKey { int kind; int64_t index; bool operator<(const DeepKey &o) const { return std::tie(kind, index) < std::tie(o.kind, o.index); } };
-enum { DK_COOD, DK_ZM, DK_CALPHA, DK_TOOD, DK_ZPT, DK_TALPHA, DK_DALPHA, DK_DBETA };
+enum { DK_ZM, DK_KZM, DK_CALPHA, DK_ZPT, DK_KZ, DK_TALPHA, DK_DALPHA, DK_DBETA };
 inline Expr deep_expression(Graph &g, const std::vector<std::pair<u64, int64_t>> &trace_arguments, u32 num_trace_cols,
                             u32 num_composition_cols, std::vector<DeepKey> &keys) {
     std::map<DeepKey, u64> index;
@@ -52,22 +55,30 @@ inline Expr deep_expression(Graph &g, const std::vector<std::pair<u64, int64_t>>
         return Hint(g, index[k]);
     };
     Expr x = X(g), one = Constant(g, 1), total;
-    std::map<DeepKey, Expr> inv_cache;
-    auto inv_x_minus = [&](int kind, int64_t i) {
-        DeepKey k{kind, i};
-        if (!inv_cache.count(k)) inv_cache[k] = one / (x - H(kind, i));
-        return inv_cache[k];
-    };
     bool first = true;
-    for (u32 j = 0; j < num_composition_cols; j++) {
-        Expr term = (Trace(g, num_trace_cols + j, 0) - H(DK_COOD, j)) * inv_x_minus(DK_ZM, 0) * H(DK_CALPHA, j);
+    auto add_group = [&](const std::vector<std::pair<u64, DeepKey>> &members, const DeepKey &konst, const DeepKey &point) {
+        if (members.empty()) return;
+        Expr acc;
+        bool f = true;
+        for (const auto &m : members) {
+            Expr term = Trace(g, m.first, 0) * H(m.second.kind, m.second.index);
+            acc = f ? term : acc + term;
+            f = false;
+        }
+        Expr term = (acc - H(konst.kind, konst.index)) * (one / (x - H(point.kind, point.index)));
         total = first ? term : total + term;
         first = false;
-    }
-    for (size_t i = 0; i < trace_arguments.size(); i++) {
-        Expr term = (Trace(g, trace_arguments[i].first, 0) - H(DK_TOOD, (int64_t)i)) * inv_x_minus(DK_ZPT, trace_arguments[i].second) * H(DK_TALPHA, (int64_t)i);
-        total = first ? term : total + term;
-        first = false;
+    };
+    std::vector<std::pair<u64, DeepKey>> members;
+    for (u32 j = 0; j < num_composition_cols; j++) members.push_back({num_trace_cols + j, DeepKey{DK_CALPHA, (int64_t)j}});
+    add_group(members, DeepKey{DK_KZM, 0}, DeepKey{DK_ZM, 0});
+    std::set<int64_t> offsets;
+    for (const auto &ta : trace_arguments) offsets.insert(ta.second);
+    for (int64_t off : offsets) {
+        members.clear();
+        for (size_t i = 0; i < trace_arguments.size(); i++)
+            if (trace_arguments[i].second == off) members.push_back({trace_arguments[i].first, DeepKey{DK_TALPHA, (int64_t)i}});
+        add_group(members, DeepKey{DK_KZ, off}, DeepKey{DK_ZPT, off});
     }
     return total * (H(DK_DALPHA, 0) + x * H(DK_DBETA, 0));
 }
@@ -218,11 +229,22 @@ public:
         std::vector<Fq> dhints;
         for (const DeepKey &k : keys) {
             switch (k.kind) {
-                case DK_COOD: dhints.push_back(proof.composition_trace_ood_evals[k.index]); break;
                 case DK_ZM: dhints.push_back(z_m); break;
+                case DK_KZM: {      // sum_j alpha'_j H_j(z^m)
+                    Fq acc;
+                    for (u64 j = 0; j < ce; j++) acc = fq_add(acc, fq_mul(co_alphas[j], proof.composition_trace_ood_evals[j]));
+                    dhints.push_back(acc);
+                    break;
+                }
                 case DK_CALPHA: dhints.push_back(co_alphas[k.index]); break;
-                case DK_TOOD: dhints.push_back(proof.execution_trace_ood_evals[k.index]); break;
                 case DK_ZPT: dhints.push_back(z_points[std::find(offsets.begin(), offsets.end(), k.index) - offsets.begin()]); break;
+                case DK_KZ: {       // sum over the arguments with this offset of alpha * T(z g^o)
+                    Fq acc;
+                    for (size_t i = 0; i < trace_args.size(); i++)
+                        if (trace_args[i].second == k.index) acc = fq_add(acc, fq_mul(ex_alphas[i], proof.execution_trace_ood_evals[i]));
+                    dhints.push_back(acc);
+                    break;
+                }
                 case DK_TALPHA: dhints.push_back(ex_alphas[k.index]); break;
                 case DK_DALPHA: dhints.push_back(d_alpha); break;
                 default: dhints.push_back(d_beta);

@@ -207,7 +207,7 @@ class Air:
             log_N = self.log_n + self.options.lde_blowup_factor.bit_length() - 1
             expr, keys = deep.deep_expression_symbolic(self.trace_arguments(), cfg.NUM_BASE_COLUMNS, cfg.NUM_EXTENSION_COLUMNS,
                                                        self.ce_blowup_factor)
-            self._deep_program = (E.compile_program(expr, cfg.NUM_BASE_COLUMNS, log_ce=log_N, symbolic=True), keys)
+            self._deep_program = (E.compile_program(expr, cfg.NUM_BASE_COLUMNS, log_ce=log_N, symbolic=True, max_live_leaves=8), keys)
         return self._deep_program
 
     def num_challenges(self):

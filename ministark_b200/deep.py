@@ -63,9 +63,16 @@ def deep_expression(trace_arguments, num_base_cols, num_ext_cols, num_compositio
 
 
 def deep_expression_symbolic(trace_arguments, num_base_cols, num_ext_cols, num_composition_cols):
-    """The same expression with every per-proof value (out-of-domain points and values, alphas, degree coefficients)
-    as a Hint placeholder, so that it is compiled ONCE per AIR (expr.compile_program(..., symbolic=True)) and bound per
-    proof (Program.bind(hints=deep_hint_values(...))).  Returns (expr, keys); keys[i] names hint i."""
+    """The same polynomial with every per-proof value as a Hint placeholder, so that it is compiled ONCE per AIR
+    (expr.compile_program(..., symbolic=True)) and bound per proof (Program.bind(hints=deep_hint_values(...))), and with
+    the terms GROUPED by their out-of-domain point:
+
+        sum_j a_j (P_j(x) - P_j(z_k)) / (x - z_k)  =  ( sum_j a_j P_j(x)  -  K_k ) / (x - z_k),   K_k = sum_j a_j P_j(z_k)
+
+    K_k is one constant per distinct point (z^m, and z g^o per trace offset o), computed on the host from the OOD values
+    the channel already holds.  Per LDE point this is one multiplication by a_j per column (Fq x Fp for a base-field
+    column: 3 base-field products) and ONE Fq x Fq product per distinct point, instead of a subtraction and two Fq x Fq
+    products per column — the same field element, hence the same words.  Returns (expr, keys); keys[i] names hint i."""
     keys, index = [], {}
 
     def H(key):
@@ -75,26 +82,40 @@ def deep_expression_symbolic(trace_arguments, num_base_cols, num_ext_cols, num_c
         return E.Hint(index[key])
 
     x = E.X()
-    inv_cache = {}
-
-    def inv_x_minus(key):
-        if key not in inv_cache:
-            inv_cache[key] = E.Constant(1) / (x - H(key))
-        return inv_cache[key]
-
-    total = None
     ncols_trace = num_base_cols + num_ext_cols
-    for j in range(num_composition_cols):
-        term = (E.Trace(ncols_trace + j, 0) - H(("cood", j))) * inv_x_minus(("zm",)) * H(("calpha", j))
-        total = term if total is None else total + term
-    for i, (col, off) in enumerate(trace_arguments):
-        term = (E.Trace(col, 0) - H(("tood", i))) * inv_x_minus(("zpt", off)) * H(("talpha", i))
+    groups = [(("zm",), ("kzm",), [(ncols_trace + j, ("calpha", j)) for j in range(num_composition_cols)])]
+    for off in sorted(set(o for _, o in trace_arguments)):
+        groups.append((("zpt", off), ("kz", off), [(col, ("talpha", i)) for i, (col, o) in enumerate(trace_arguments) if o == off]))
+    total = None
+    for point, konst, members in groups:
+        if not members:
+            continue
+        acc = None
+        for col, alpha in members:
+            term = E.Trace(col, 0) * H(alpha)
+            acc = term if acc is None else acc + term
+        term = (acc - H(konst)) * (E.Constant(1) / (x - H(point)))
         total = term if total is None else total + term
     return total * (H(("dalpha",)) + x * H(("dbeta",))), keys
 
 
-def deep_hint_values(keys, z_points, z_m, trace_oods, composition_oods, trace_alphas, composition_alphas, degree_alpha, degree_beta):
+def deep_hint_values(keys, z_points, z_m, trace_oods, composition_oods, trace_alphas, composition_alphas, degree_alpha, degree_beta,
+                     trace_arguments=None):
+    """values of the hints `keys` names.  trace_arguments (the list the expression was built from) is needed for the
+    per-offset constants K_o = sum over the arguments with offset o of alpha * ood."""
+    def dot(pairs):
+        acc = (0, 0, 0)
+        for a, v in pairs:
+            acc = E.q_add(acc, E.q_mul(tuple(a), tuple(v)))
+        return acc
+
+    def kz(off):
+        if trace_arguments is None:
+            raise ValueError("deep_hint_values: trace_arguments is required for the grouped DEEP expression")
+        return dot((trace_alphas[i], trace_oods[i]) for i, (_, o) in enumerate(trace_arguments) if o == off)
+
     table = {"zm": lambda: z_m, "dalpha": lambda: degree_alpha, "dbeta": lambda: degree_beta,
              "zpt": lambda off: z_points[off], "tood": lambda i: trace_oods[i], "cood": lambda j: composition_oods[j],
-             "talpha": lambda i: trace_alphas[i], "calpha": lambda j: composition_alphas[j]}
+             "talpha": lambda i: trace_alphas[i], "calpha": lambda j: composition_alphas[j],
+             "kzm": lambda: dot(zip(composition_alphas, composition_oods)), "kz": kz}
     return [tuple(table[k[0]](*k[1:])) for k in keys]

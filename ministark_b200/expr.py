@@ -201,8 +201,12 @@ def periodic_tables(ctx, program, log_n, lde_step, offset_canonical=7):
 
 
 def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, log_ce=None, fold_pow0=True, symbolic=False,
-                    num_cols=None):
+                    num_cols=None, max_live_leaves=None):
     """Flatten `expr` into the evaluator's linear program.
+
+    max_live_leaves: keep at most this many leaf values (trace cells, constants, x) in registers; beyond it the least
+    recently used one is dropped and loaded again at its next use.  A sum that names every column twice (the grouped
+    DEEP expression, deep.py) then runs in a dozen registers instead of one per column.
 
     num_cols: total number of trace columns (base + extension); periodic tables take the column slots after them
     (required when the expression has Periodic leaves).
@@ -350,6 +354,14 @@ def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, lo
         return reg_of.pop(k)
 
     def emit_leaf(x):
+        if max_live_leaves is not None:
+            while len(leaf_regs) >= max_live_leaves:
+                victims = [k for k in leaf_regs if k not in pinned]
+                if not victims:
+                    break
+                k = min(victims, key=lambda v: touch.get(v, -1))
+                del leaf_regs[k]
+                free.append(reg_of.pop(k))
         r = alloc()
         if id(x) in cval:
             code.append([OP_CONST | (typ[id(x)] << 8), r, const_slot(cval[id(x)]), 0])

@@ -320,7 +320,8 @@ class GpuProver:
         dprog_sym, dkeys = air.deep_program()
         dprog = dprog_sym.bind(hints=deep.deep_hint_values(
             dkeys, z_points, z_m, [_lift(v) for v in execution_trace_oods], [_lift(v) for v in composition_trace_oods],
-            [_lift(v) for v in ex_alphas], [_lift(v) for v in co_alphas], _lift(d_alpha), _lift(d_beta)))
+            [_lift(v) for v in ex_alphas], [_lift(v) for v in co_alphas], _lift(d_alpha), _lift(d_beta),
+            trace_arguments=trace_arguments))
         ncols_all = nbase + next_ + ce_blowup
         sz = N * 8
         cols = [base_lde.data_ptr() + c * sz for c in range(nbase)]

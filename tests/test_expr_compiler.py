@@ -106,7 +106,7 @@ def test_deep_program_symbolic_equals_plain(which):
     plain = E.compile_program(deep.deep_expression(args, nb, ne, nc, z_points, z_m, toods, coods, talphas, calphas, da, db), nb,
                               log_ce=m.bit_length() - 1)
     sym, keys = air.deep_program()
-    bound = sym.bind(hints=deep.deep_hint_values(keys, z_points, z_m, toods, coods, talphas, calphas, da, db))
+    bound = sym.bind(hints=deep.deep_hint_values(keys, z_points, z_m, toods, coods, talphas, calphas, da, db, trace_arguments=args))
     for row in (0, 7, m - 1):
         x = rng.randrange(2, P)
         assert run_program(bound, x, cols, is_q, row, m) == run_program(plain, x, cols, is_q, row, m)
