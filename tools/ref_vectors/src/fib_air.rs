@@ -6,6 +6,7 @@ use ark_serialize::CanonicalSerialize;
 use ministark::air::AirConfig;
 use ministark::challenges::Challenges;
 use ministark::constraints::{AlgebraicItem, Constraint, ExecutionTraceColumn};
+use ministark::expression::Expr;
 use ministark::hash::{HashFn, Sha256HashFn};
 use ministark::hints::Hints;
 use ministark::merkle::MatrixMerkleTreeImpl;
@@ -68,19 +69,12 @@ impl AirConfig for FibAir {
             (7.curr() - v7) / (X - first),
         ];
         cs.push((7.curr() - Hint(0)) / (X - last));
-        let step = vec![
-            0.next() - 6.curr() * 7.curr(),
-            1.next() - 7.curr() * 0.next(),
-            2.next() - 0.next() * 1.next(),
-            3.next() - 1.next() * 2.next(),
-            4.next() - 2.next() * 3.next(),
-            5.next() - 3.next() * 4.next(),
-            6.next() - 4.next() * 5.next(),
-            7.next() - 5.next() * 6.next(),
-        ];
-        for c in step {
+        // sequence value j of a row pair: the current row holds 0..8, the next row 8..16; v_(c+8) = v_(c+6) * v_(c+7)
+        let cell = |j: usize| -> Expr<AlgebraicItem<FieldVariant<Fp, Fp>>> { if j < 8 { j.curr() } else { (j - 8).next() } };
+        for c in 0..8usize {
+            let step = cell(c + 8) - cell(c + 6) * cell(c + 7);
             // every row but the last: (x - t_(n-1)) / (x^n - 1)
-            cs.push(c * ((X - last) / (X.pow(trace_len) - one)));
+            cs.push(step * ((X - last) / (X.pow(trace_len) - one)));
         }
         cs.into_iter().map(Constraint::new).collect()
     }
