@@ -220,6 +220,7 @@ def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, lo
     lde_step * off (eval_cpu.rs:119-123).  The result is always stored as an Fq element.
     """
     order, seen = [], set()
+    trace_len = (1 << log_ce) // lde_step if log_ce is not None and lde_step >= 1 else 0
 
     def visit(e):                      # iterative post-order (DAGs can be deep)
         # Sethi-Ullman flavoured order: the operand with the larger subtree is evaluated first, so a long
@@ -269,6 +270,15 @@ def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, lo
             args = tuple(rewritten[id(a)] if isinstance(a, Expr) else a for a in node.args)
             if node.kind == "div":
                 rewritten[id(node)] = Expr("mul", args[0], Expr("inv", args[1]))
+            elif node.kind == "pow" and args[0].kind == "x" and trace_len and args[1] >= 2 * trace_len and args[1] % trace_len < 64:
+                # degree adjustments are x^(a n + b) with a < ce_blowup and a small b (src/air.rs:50-82): computed as
+                # (x^n)^a * x^b they share the log2(n) squarings of x^n — which the zerofier needs anyway — instead of
+                # paying ~1.5 log2(a n) multiplications each
+                a_, b_ = divmod(args[1], trace_len)
+                v = Expr("pow", Expr("pow", args[0], trace_len), a_) if a_ > 1 else Expr("pow", args[0], trace_len)
+                if b_:
+                    v = Expr("mul", v, Expr("pow", args[0], b_) if b_ > 1 else args[0])
+                rewritten[id(node)] = v
             else:
                 rewritten[id(node)] = Expr(node.kind, *args)
             stack.pop()
