@@ -197,7 +197,8 @@ class Air:
             cfg = self.config
             log_ce = self.log_n + self.ce_blowup_factor.bit_length() - 1
             self._composition_program = E.compile_program(self.composition_constraint, cfg.NUM_BASE_COLUMNS,
-                                                          lde_step=self.ce_blowup_factor, log_ce=log_ce, symbolic=True)
+                                                          lde_step=self.ce_blowup_factor, log_ce=log_ce, symbolic=True,
+                                                          batch_inverses=True)   # zerofier denominators: never 0 on the LDE coset
         return self._composition_program
 
     def deep_program(self):
@@ -207,7 +208,8 @@ class Air:
             log_N = self.log_n + self.options.lde_blowup_factor.bit_length() - 1
             expr, keys = deep.deep_expression_symbolic(self.trace_arguments(), cfg.NUM_BASE_COLUMNS, cfg.NUM_EXTENSION_COLUMNS,
                                                        self.ce_blowup_factor)
-            self._deep_program = (E.compile_program(expr, cfg.NUM_BASE_COLUMNS, log_ce=log_N, symbolic=True, max_live_leaves=8), keys)
+            self._deep_program = (E.compile_program(expr, cfg.NUM_BASE_COLUMNS, log_ce=log_N, symbolic=True, max_live_leaves=8,
+                                                    batch_inverses=True), keys)
         return self._deep_program
 
     def num_challenges(self):

@@ -200,9 +200,77 @@ def periodic_tables(ctx, program, log_n, lde_step, offset_canonical=7):
     return out
 
 
+def _batch_inverses(root, num_base_cols):
+    """Montgomery's trick inside one evaluation point: the inverses 1/d_1 .. 1/d_k of the program (operands that vary with
+    the point and contain no inverse themselves, grouped by field) become ONE inversion of d_1 ... d_k and 3(k - 1)
+    multiplications.  An inversion is a ~72-multiplication Fermat chain, so the three denominators of a composition
+    constraint ((x - t_0), (x^n - 1), (x - t_(n-1))) or of the DEEP polynomial cost one chain instead of three.
+    Valid when no operand vanishes on the evaluation domain — true for zerofier denominators over the LDE coset, which is
+    disjoint from the trace domain, and (as for the reference's own formulas) for x - z with z out of domain; with a
+    zero operand EVERY inverse of the batch would come out 0 where the reference's batch inversion skips zeros
+    (src/eval_cpu.rs:280-295), so generic user expressions keep their independent inversions (the default)."""
+    post, seen, stack = [], set(), [(root, False)]
+    while stack:
+        node, done = stack.pop()
+        if done:
+            post.append(node)
+            continue
+        if id(node) in seen:
+            continue
+        seen.add(id(node))
+        stack.append((node, True))
+        stack.extend((a, False) for a in node.args if isinstance(a, Expr) and id(a) not in seen)
+    has_inv, varies, typ = {}, {}, {}
+    for nd in post:
+        kids = [a for a in nd.args if isinstance(a, Expr)]
+        has_inv[id(nd)] = nd.kind == "inv" or any(has_inv[id(k)] for k in kids)
+        varies[id(nd)] = nd.kind in ("x", "trace", "periodic") or any(varies[id(k)] for k in kids)
+        if nd.kind == "const":
+            typ[id(nd)] = FQ if nd.args[1] else FP
+        elif nd.kind in _SYMBOLIC or nd.kind in ("chal", "hint"):
+            typ[id(nd)] = FQ
+        elif nd.kind == "x":
+            typ[id(nd)] = FP
+        elif nd.kind == "trace":
+            typ[id(nd)] = FP if nd.args[0] < num_base_cols else FQ
+        elif nd.kind == "periodic":
+            typ[id(nd)] = FQ if any(isinstance(c, tuple) for c in nd.args[0]) else FP
+        else:
+            typ[id(nd)] = max(typ[id(k)] for k in kids)
+    groups = {}
+    for nd in post:
+        if nd.kind == "inv" and varies[id(nd.args[0])] and not has_inv[id(nd.args[0])]:
+            groups.setdefault(typ[id(nd)], []).append(nd)
+    repl = {}
+    for members in groups.values():
+        if len(members) < 2:
+            continue
+        ds = [m.args[0] for m in members]
+        prefix = [ds[0]]
+        for d in ds[1:]:
+            prefix.append(Expr("mul", prefix[-1], d))
+        inv = Expr("inv", prefix[-1])
+        for i in range(len(ds) - 1, 0, -1):
+            repl[id(members[i])] = Expr("mul", inv, prefix[i - 1])
+            inv = Expr("mul", inv, ds[i])
+        repl[id(members[0])] = inv
+    if not repl:
+        return root
+    rebuilt = {}
+    for nd in post:
+        if id(nd) in repl:
+            rebuilt[id(nd)] = repl[id(nd)]
+        else:
+            rebuilt[id(nd)] = Expr(nd.kind, *[rebuilt[id(a)] if isinstance(a, Expr) else a for a in nd.args])
+    return rebuilt[id(root)]
+
+
 def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, log_ce=None, fold_pow0=True, symbolic=False,
-                    num_cols=None, max_live_leaves=None):
+                    num_cols=None, max_live_leaves=None, batch_inverses=False):
     """Flatten `expr` into the evaluator's linear program.
+
+    batch_inverses: see _batch_inverses — for programs whose denominators cannot vanish on the evaluation domain (the
+    AIR composition and DEEP programs built by air.py).
 
     max_live_leaves: keep at most this many leaf values (trace cells, constants, x) in registers; beyond it the least
     recently used one is dropped and loaded again at its next use.  A sum that names every column twice (the grouped
@@ -285,6 +353,8 @@ def compile_program(expr, num_base_cols, challenges=(), hints=(), lde_step=1, lo
         return rewritten[id(e)]
 
     expr = rewrite(expr)
+    if batch_inverses:
+        expr = _batch_inverses(expr, num_base_cols)
     visit(expr)
     # constant folding + typing
     cval, typ = {}, {}

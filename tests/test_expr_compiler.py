@@ -43,6 +43,42 @@ def test_random_expressions(seed):
         assert run_program(sym, x, cols, is_q, row, m) == want
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_batched_inverses_and_shared_powers(seed):
+    """compile_program(batch_inverses=True): the inverses of one point through ONE inversion (Montgomery's trick), Fp and
+    Fq denominators in separate batches, an inverse under an inverse left alone; and x^(a n + b) rewritten to
+    (x^n)^a * x^b.  Same values as the direct evaluation whenever no denominator vanishes (random operands)."""
+    rng = random.Random(100 + seed)
+    nbase, next_, m, lde_step = 4, 2, 32, 4
+    n = m // lde_step
+    cols, is_q = random_columns(rng, nbase, next_, m)
+    x = E.X()
+    T = E.Trace
+    fp_dens = [x - E.Constant(rng.randrange(P)), x ** n - E.Constant(1), T(0, 0) + T(1, 1) * x, T(2, 0) * T(3, 1) + E.Constant(3)]
+    fq_dens = [x - E.Hint(0), T(4, 0) + E.Challenge(0), T(5, 1) * x + T(4, 1)]
+    rng.shuffle(fp_dens)
+    rng.shuffle(fq_dens)
+    expr = None
+    for k, d in enumerate(fp_dens[:3] + fq_dens[:2 + seed % 2]):
+        term = (T(k % 4, 0) + E.Constant(k)) / d * (x ** ((3 + k) * n + k) * E.Challenge(0) + E.Hint(0))
+        expr = term if expr is None else expr + term
+    expr = expr + E.Constant(7) / (x + E.Constant(1) / (x - E.Constant(5)))          # an inverse under an inverse
+    ch, hi = [tuple(rng.randrange(P) for _ in range(3))], [tuple(rng.randrange(P) for _ in range(3))]
+    log_ce = m.bit_length() - 1
+    plain = E.compile_program(expr, nbase, challenges=ch, hints=hi, lde_step=lde_step, log_ce=log_ce)
+    batched = E.compile_program(expr, nbase, challenges=ch, hints=hi, lde_step=lde_step, log_ce=log_ce, batch_inverses=True)
+    sym = E.compile_program(expr, nbase, lde_step=lde_step, log_ce=log_ce, symbolic=True, batch_inverses=True, max_live_leaves=4)
+    sym = sym.bind(challenges=ch, hints=hi)
+    count = lambda prog, op: int(sum(1 for ins in prog.code if ins[0] & 0xff == op))
+    assert count(plain, E.OP_INV) >= 7 and count(batched, E.OP_INV) == 3            # the Fp batch (with the inner 1/(x - 5)), the Fq batch, the outer inverse
+    assert max(int(ins[3]) for ins in batched.code if ins[0] & 0xff == E.OP_POW) <= n   # no exponent beyond x^n is left
+    for row in range(0, m, 5):
+        xv = rng.randrange(1, P)
+        want = direct(expr, xv, cols, row, m, ch, hi, lde_step=lde_step)
+        for prog in (plain, batched, sym):
+            assert run_program(prog, xv, cols, is_q, row, m) == want
+
+
 @pytest.mark.parametrize("which", ["fib", "perm", "brainfuck"])
 def test_composition_programs_of_the_example_airs(which):
     """the real compositions: brainfuck's 48 constraints need leaf rematerialisation to fit 48 registers"""
