@@ -205,10 +205,12 @@ def _batch_inverses(root, num_base_cols):
     the point and contain no inverse themselves, grouped by field) become ONE inversion of d_1 ... d_k and 3(k - 1)
     multiplications.  An inversion is a ~72-multiplication Fermat chain, so the three denominators of a composition
     constraint ((x - t_0), (x^n - 1), (x - t_(n-1))) or of the DEEP polynomial cost one chain instead of three.
-    Valid when no operand vanishes on the evaluation domain — true for zerofier denominators over the LDE coset, which is
-    disjoint from the trace domain, and (as for the reference's own formulas) for x - z with z out of domain; with a
-    zero operand EVERY inverse of the batch would come out 0 where the reference's batch inversion skips zeros
-    (src/eval_cpu.rs:280-295), so generic user expressions keep their independent inversions (the default)."""
+    Only denominators that are functions of the point alone (x, constants, periodic columns) are batched — a denominator
+    that reads a trace cell keeps its own inversion.  Valid when no batched operand vanishes on the evaluation domain:
+    true for zerofier denominators over the LDE coset, which is disjoint from the trace domain, and (as for the
+    reference's own formulas) for x - z with z out of domain; with a zero operand EVERY inverse of the batch would come
+    out 0 where the reference's batch inversion skips zeros (src/eval_cpu.rs:280-295), so generic user expressions keep
+    their independent inversions (the default)."""
     post, seen, stack = [], set(), [(root, False)]
     while stack:
         node, done = stack.pop()
@@ -220,11 +222,12 @@ def _batch_inverses(root, num_base_cols):
         seen.add(id(node))
         stack.append((node, True))
         stack.extend((a, False) for a in node.args if isinstance(a, Expr) and id(a) not in seen)
-    has_inv, varies, typ = {}, {}, {}
+    has_inv, varies, reads_trace, typ = {}, {}, {}, {}
     for nd in post:
         kids = [a for a in nd.args if isinstance(a, Expr)]
         has_inv[id(nd)] = nd.kind == "inv" or any(has_inv[id(k)] for k in kids)
         varies[id(nd)] = nd.kind in ("x", "trace", "periodic") or any(varies[id(k)] for k in kids)
+        reads_trace[id(nd)] = nd.kind == "trace" or any(reads_trace[id(k)] for k in kids)
         if nd.kind == "const":
             typ[id(nd)] = FQ if nd.args[1] else FP
         elif nd.kind in _SYMBOLIC or nd.kind in ("chal", "hint"):
@@ -239,7 +242,7 @@ def _batch_inverses(root, num_base_cols):
             typ[id(nd)] = max(typ[id(k)] for k in kids)
     groups = {}
     for nd in post:
-        if nd.kind == "inv" and varies[id(nd.args[0])] and not has_inv[id(nd.args[0])]:
+        if nd.kind == "inv" and varies[id(nd.args[0])] and not has_inv[id(nd.args[0])] and not reads_trace[id(nd.args[0])]:
             groups.setdefault(typ[id(nd)], []).append(nd)
     repl = {}
     for members in groups.values():

@@ -46,7 +46,8 @@ def test_random_expressions(seed):
 @pytest.mark.parametrize("seed", range(6))
 def test_batched_inverses_and_shared_powers(seed):
     """compile_program(batch_inverses=True): the inverses of one point through ONE inversion (Montgomery's trick), Fp and
-    Fq denominators in separate batches, an inverse under an inverse left alone; and x^(a n + b) rewritten to
+    Fq denominators in separate batches, denominators that read the trace and an inverse under an inverse left alone; and
+    x^(a n + b) rewritten to
     (x^n)^a * x^b.  Same values as the direct evaluation whenever no denominator vanishes (random operands)."""
     rng = random.Random(100 + seed)
     nbase, next_, m, lde_step = 4, 2, 32, 4
@@ -54,12 +55,10 @@ def test_batched_inverses_and_shared_powers(seed):
     cols, is_q = random_columns(rng, nbase, next_, m)
     x = E.X()
     T = E.Trace
-    fp_dens = [x - E.Constant(rng.randrange(P)), x ** n - E.Constant(1), T(0, 0) + T(1, 1) * x, T(2, 0) * T(3, 1) + E.Constant(3)]
-    fq_dens = [x - E.Hint(0), T(4, 0) + E.Challenge(0), T(5, 1) * x + T(4, 1)]
-    rng.shuffle(fp_dens)
-    rng.shuffle(fq_dens)
+    fp_dens = [x - E.Constant(rng.randrange(P)), x ** n - E.Constant(1), x * x + E.Constant(3), T(2, 0) * T(3, 1) + x]
+    fq_dens = [x - E.Hint(0), x * E.Challenge(0) + E.Constant(9), T(5, 1) * x + T(4, 1)]
     expr = None
-    for k, d in enumerate(fp_dens[:3] + fq_dens[:2 + seed % 2]):
+    for k, d in enumerate(fp_dens + fq_dens):
         term = (T(k % 4, 0) + E.Constant(k)) / d * (x ** ((3 + k) * n + k) * E.Challenge(0) + E.Hint(0))
         expr = term if expr is None else expr + term
     expr = expr + E.Constant(7) / (x + E.Constant(1) / (x - E.Constant(5)))          # an inverse under an inverse
@@ -70,8 +69,10 @@ def test_batched_inverses_and_shared_powers(seed):
     sym = E.compile_program(expr, nbase, lde_step=lde_step, log_ce=log_ce, symbolic=True, batch_inverses=True, max_live_leaves=4)
     sym = sym.bind(challenges=ch, hints=hi)
     count = lambda prog, op: int(sum(1 for ins in prog.code if ins[0] & 0xff == op))
-    assert count(plain, E.OP_INV) >= 7 and count(batched, E.OP_INV) == 3            # the Fp batch (with the inner 1/(x - 5)), the Fq batch, the outer inverse
-    assert max(int(ins[3]) for ins in batched.code if ins[0] & 0xff == E.OP_POW) <= n   # no exponent beyond x^n is left
+    # 9 inversions; batched: one for the Fp denominators in x alone (with the inner 1/(x - 5)), one for the Fq ones, the
+    # two denominators that read trace cells keep their own, and so does the outer inverse
+    assert count(plain, E.OP_INV) == 9 and count(batched, E.OP_INV) == 5
+    assert max(int(ins[3]) for ins in batched.code if ins[0] & 0xff == E.OP_POW) < 2 * n   # every x^(a n + b) was split: only x^n, a and b are left as exponents
     for row in range(0, m, 5):
         xv = rng.randrange(1, P)
         want = direct(expr, xv, cols, row, m, ch, hi, lde_step=lde_step)
