@@ -438,17 +438,78 @@ struct Program {
 // Flatten the DAG under `root` into the evaluator's linear program (the algorithm of ministark_b200/expr.py::compile_program
 // with symbolic = true): a / b -> a * inv(b) with shared inverses; constant folding; largest-operand-first post order;
 // registers by liveness with least-recently-used eviction of rematerialisable leaves (x, trace loads, constants).
-inline Program compile_program(Graph &g, int root, u32 num_base_cols, u64 lde_step, int log_ce) {
-    // ---- rewrite Div
+// Montgomery's trick inside one evaluation point (ministark_b200/expr.py::_batch_inverses): the inverses 1/d_1 .. 1/d_k whose
+// operands are functions of the point alone (x, constants; no trace cell, no inverse inside) become ONE inversion of
+// d_1 ... d_k and 3(k - 1) multiplications, per field.  For programs whose denominators cannot vanish on the evaluation
+// domain (the AIR composition and the DEEP polynomial over the LDE coset): with a zero operand every inverse of the batch
+// would come out 0, where independent inversions only zero their own term (src/eval_cpu.rs:280-295).
+inline int batch_inverses_pass(Graph &g, int root, u32 num_base_cols) {
+    const std::vector<int> post = post_order(g, root, false);
+    std::map<int, char> has_inv, varies, reads_trace, typ;
+    for (int n : post) {
+        const Node &nd = g.nodes[n];
+        const bool ka = nd.a >= 0, kb = nd.b >= 0;
+        has_inv[n] = nd.kind == K_INV || (ka && has_inv[nd.a]) || (kb && has_inv[nd.b]);
+        varies[n] = nd.kind == K_X || nd.kind == K_TRACE || (ka && varies[nd.a]) || (kb && varies[nd.b]);
+        reads_trace[n] = nd.kind == K_TRACE || (ka && reads_trace[nd.a]) || (kb && reads_trace[nd.b]);
+        switch (nd.kind) {
+            case K_CONST: typ[n] = nd.ext; break;
+            case K_CHAL: case K_HINT: case K_CCOEF: typ[n] = 1; break;
+            case K_X: typ[n] = 0; break;
+            case K_TRACE: typ[n] = nd.k[0] >= num_base_cols; break;
+            default: typ[n] = std::max(ka ? typ[nd.a] : (char)0, kb ? typ[nd.b] : (char)0);
+        }
+    }
+    std::map<int, int> repl;
+    for (char field = 0; field < 2; field++) {
+        std::vector<int> members;
+        for (int n : post)
+            if (g.nodes[n].kind == K_INV && typ[n] == field && varies[g.nodes[n].a] && !has_inv[g.nodes[n].a] && !reads_trace[g.nodes[n].a])
+                members.push_back(n);
+        if (members.size() < 2) continue;
+        std::vector<int> ds, prefix;
+        for (int m : members) ds.push_back(g.nodes[m].a);
+        prefix.push_back(ds[0]);
+        for (size_t i = 1; i < ds.size(); i++) prefix.push_back(g.mk(K_MUL, prefix.back(), ds[i]));
+        int inv = g.mk(K_INV, prefix.back());
+        for (size_t i = ds.size() - 1; i >= 1; i--) {
+            repl[members[i]] = g.mk(K_MUL, inv, prefix[i - 1]);
+            inv = g.mk(K_MUL, inv, ds[i]);
+        }
+        repl[members[0]] = inv;
+    }
+    if (repl.empty()) return root;
+    std::map<int, int> rebuilt;
+    for (int n : post) {
+        if (repl.count(n)) { rebuilt[n] = repl[n]; continue; }
+        const Node nd = g.nodes[n];
+        rebuilt[n] = g.mk(nd.kind, nd.a >= 0 ? rebuilt[nd.a] : -1, nd.b >= 0 ? rebuilt[nd.b] : -1, nd.k[0], nd.k[1], nd.k[2], nd.ext);
+    }
+    return rebuilt[root];
+}
+
+inline Program compile_program(Graph &g, int root, u32 num_base_cols, u64 lde_step, int log_ce, bool batch_inverses = false) {
+    // ---- rewrite Div; split the degree-adjustment powers x^(a n + b) into (x^n)^a * x^b, which share the squarings of x^n
+    const u64 trace_len = (log_ce >= 0 && lde_step >= 1) ? (((u64)1 << log_ce) / lde_step) : 0;
     std::vector<int> rew(g.nodes.size(), -1);
     for (int n : post_order(g, root, false)) {
         const Node nd = g.nodes[n];
         const int a = nd.a >= 0 ? rew[nd.a] : -1, b = nd.b >= 0 ? rew[nd.b] : -1;
-        if (nd.kind == K_DIV) rew[n] = g.mk(K_MUL, a, g.mk(K_INV, b));
-        else rew[n] = g.mk(nd.kind, a, b, nd.k[0], nd.k[1], nd.k[2], nd.ext);
+        if (nd.kind == K_DIV) {
+            rew[n] = g.mk(K_MUL, a, g.mk(K_INV, b));
+        } else if (nd.kind == K_POW && g.nodes[a].kind == K_X && trace_len && nd.k[0] >= 2 * trace_len && nd.k[0] % trace_len < 64) {
+            const u64 a_ = nd.k[0] / trace_len, b_ = nd.k[0] % trace_len;
+            int v = g.mk(K_POW, a, -1, trace_len);
+            if (a_ > 1) v = g.mk(K_POW, v, -1, a_);
+            if (b_) v = g.mk(K_MUL, v, b_ > 1 ? g.mk(K_POW, a, -1, b_) : a);
+            rew[n] = v;
+        } else {
+            rew[n] = g.mk(nd.kind, a, b, nd.k[0], nd.k[1], nd.k[2], nd.ext);
+        }
         if (rew.size() < g.nodes.size()) rew.resize(g.nodes.size(), -1);
     }
     root = rew[root];
+    if (batch_inverses) root = batch_inverses_pass(g, root, num_base_cols);
     const std::vector<int> order = post_order(g, root, true);
     // ---- constant folding + typing (0 = Fp, 1 = Fq)
     const size_t NN = g.nodes.size();
@@ -636,7 +697,7 @@ public:
     }
     Program composition_program(u32 num_base_cols) {
         int log_ce = (int)log_n + (63 - __builtin_clzll(ce_blowup_factor));
-        return compile_program(g, composition.id, num_base_cols, ce_blowup_factor, log_ce);
+        return compile_program(g, composition.id, num_base_cols, ce_blowup_factor, log_ce, /*batch_inverses=*/true);   // zerofier denominators
     }
 };
 

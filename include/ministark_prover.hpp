@@ -250,7 +250,7 @@ public:
                 default: dhints.push_back(d_beta);
             }
         }
-        const Program dprog = compile_program(dg, dexpr.id, nbase, 1, (int)log_N).bind({}, dhints, {});
+        const Program dprog = compile_program(dg, dexpr.id, nbase, 1, (int)log_N, /*batch_inverses=*/true).bind({}, dhints, {});
         std::vector<const void *> cols;
         std::vector<int> is_q;
         for (u32 c = 0; c < nbase; c++) { cols.push_back(base_lde.words() + (size_t)c * N); is_q.push_back(0); }
