@@ -132,3 +132,23 @@ def test_generated_kernel_source_runs_like_the_interpreter(tmp_path, orc, cpu_ab
     kernel.run_all(ptrs, C.c_void_p(consts.ctypes.data), C.c_void_p(lo.ctypes.data), C.c_void_p(hi.ctypes.data), C.c_uint(len(hi)),
                    C.c_uint64(GENERATOR), C.c_uint(log_m), 1, out_bitrev, C.c_void_p(got.ctypes.data))
     assert want.any() and np.array_equal(got, want)
+
+
+def test_generated_kernel_source_of_the_config3_program(tmp_path, orc, cpu_abi):
+    """the synthetic AIR of BASELINE config 3 (ministark_b200/synth_air.py): the specialised kernel's source run on the host
+    reproduces oracle/synth_oracle.py's constraint column, read in place from the bit-reversed LDE prefix"""
+    from ministark_b200 import synth_air
+    from oracle import synth_oracle
+    log_n, log_b, ncols = 8, 3, 32
+    trace = orc.rand_matrix(ncols, 1 << log_n, 1, seed=9)
+    lde = orc.lde(orc.ntt(trace, 1, log_n, inverse=True), 1, log_n, log_b, orc.generator(), True)
+    prog = E.compile_program(synth_air.composition(ncols, log_n, 1), ncols, lde_step=1, log_ce=log_n)
+    kernel = _host_kernel(str(tmp_path), prog, 1)
+    cols = [np.ascontiguousarray(c[:1 << log_n]) for c in lde]       # the ce-domain prefix of every LDE column
+    ptrs = (C.c_void_p * ncols)(*[c.ctypes.data for c in cols])
+    lo, hi = _tables(log_n)
+    consts = np.ascontiguousarray(prog.consts)
+    got = np.zeros(1 << log_n, dtype=np.uint64)
+    kernel.run_all(ptrs, C.c_void_p(consts.ctypes.data), C.c_void_p(lo.ctypes.data), C.c_void_p(hi.ctypes.data), C.c_uint(len(hi)),
+                   C.c_uint64(GENERATOR), C.c_uint(log_n), 1, 0, C.c_void_p(got.ctypes.data))
+    assert np.array_equal(got, synth_oracle.constraint_eval(orc, lde, log_n, log_b, ncols))
