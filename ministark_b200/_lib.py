@@ -87,5 +87,7 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        if b"sm_100a" not in lib.ms_version():      # only the CUDA build is ever used: there is no CPU path in the product
+            raise RuntimeError(f"{LIB_PATH} is not the sm_100a build of libministark_b200 ({lib.ms_version()!r})")
         _lib = lib
     return _lib

@@ -180,8 +180,10 @@ def test_python_prover_on_bad_inputs(orc):
 
 def test_harness_is_not_reachable_from_the_product():
     """the loader the product uses opens only its own library; the harness lives under tests/ and is installed explicitly"""
+    import inspect
     from ministark_b200 import _lib
     assert _lib.LIB_PATH.endswith("libministark_b200.so") and not getattr(_lib, "_cpu_device_installed", False)
+    assert 'b"sm_100a" not in lib.ms_version()' in inspect.getsource(_lib.load)      # the loader insists on the CUDA build
     for dirpath, _, files in os.walk(os.path.join(ROOT, "ministark_b200")):
         for f in files:
             if f.endswith(".py"):
