@@ -212,23 +212,31 @@ class Air:
                                                     batch_inverses=True), keys)
         return self._deep_program
 
+    # the three walks below depend on the constraints only: done once per Air (the provers copy a cached Air per proof,
+    # and each walk of the brainfuck AIR costs ~0.5 ms of a 10 ms proof)
     def num_challenges(self):
-        idx = [a[0] for c in self.constraints for a in _leaves(c, "chal")]
-        return max(idx) + 1 if idx else 0
+        if getattr(self, "_num_challenges", None) is None:
+            idx = [a[0] for c in self.constraints for a in _leaves(c, "chal")]
+            self._num_challenges = max(idx) + 1 if idx else 0
+        return self._num_challenges
 
     def num_composition_constraint_coeffs(self):
-        idx = [a[0] for a in _leaves(self.composition_constraint, "ccoef")]
-        return max(idx) + 1 if idx else 0
+        if getattr(self, "_num_ccoefs", None) is None:
+            idx = [a[0] for a in _leaves(self.composition_constraint, "ccoef")]
+            self._num_ccoefs = max(idx) + 1 if idx else 0
+        return self._num_ccoefs
 
     def gen_hints(self, challenges):
         return self.config.gen_hints(self.trace_len, self.public_inputs, challenges)
 
     def trace_arguments(self):
         """BTreeSet<(column, offset)> — sorted by column, then signed offset (src/air.rs:240-246)"""
-        args = set()
-        for c in self.constraints:
-            args |= _leaves(c, "trace")
-        return sorted(args)
+        if getattr(self, "_trace_arguments", None) is None:
+            args = set()
+            for c in self.constraints:
+                args |= _leaves(c, "trace")
+            self._trace_arguments = sorted(args)
+        return list(self._trace_arguments)
 
     def substitute_composition_coeffs(self, coeffs):
         """the map_leaves of AirConfig::eval_constraint (src/air.rs:96-101): CompositionCoeff(i) -> Constant"""

@@ -285,6 +285,9 @@ class BrainfuckTrace(Trace):
         return out
 
 
+_FACTOR_PROGRAMS = {}
+
+
 def _device_extension(trace, ch, ctx, base_dev):
     """The nine extension columns of `BrainfuckTrace._extension`, built on the device: every column is
     x_0 = init, x_(i+1) = x_i * a_i + b_i  with per-row multipliers / addends that are pointwise expressions of the
@@ -310,8 +313,10 @@ def _device_extension(trace, ch, ctx, base_dev):
 
     def evaluate(expr):
         out = torch.empty(sz, dtype=torch.int64, device=base_dev.device)
-        prog = E.compile_program(expr, len(cols), challenges=ch)
-        ctx.eval_constraints_ptrs(prog, out, log_n, cols, is_q, fq_field=FQ3, offset=ONE)
+        prog = _FACTOR_PROGRAMS.get(id(expr))               # the factor expressions do not depend on the proof: compiled once
+        if prog is None:                                    # (hash-consed Expr nodes live as long as the process)
+            prog = _FACTOR_PROGRAMS[id(expr)] = E.compile_program(expr, len(cols), symbolic=True)
+        ctx.eval_constraints_ptrs(prog.bind(challenges=ch), out, log_n, cols, is_q, fq_field=FQ3, offset=ONE)
         return out
 
     mont3 = lambda v: np.array([c * _R % P for c in v], dtype=np.uint64)

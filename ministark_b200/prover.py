@@ -198,6 +198,7 @@ class GpuProver:
             self._airs[key] = Air(cfg, n, None, options)
             self._airs[key].composition_program()
             self._airs[key].deep_program()
+            self._airs[key].num_challenges(), self._airs[key].num_composition_constraint_coeffs(), self._airs[key].trace_arguments()
         air = copy.copy(self._airs[key])
         air.public_inputs = stark.get_public_inputs()
         channel = ProverChannel(air, stark.gen_public_coin(air), ctx)

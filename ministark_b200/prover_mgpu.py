@@ -357,7 +357,8 @@ class ShardedProver(GpuProver):
             air0.deep_program()
             # the composition evaluated block by block: inside a block the ce-domain stride is 1 and the domain has n points
             air0._block_program = E.compile_program(air0.composition_constraint, cfg.NUM_BASE_COLUMNS, lde_step=1,
-                                                    log_ce=air0.log_n, symbolic=True)
+                                                    log_ce=air0.log_n, symbolic=True, batch_inverses=True)
+            air0.num_challenges(), air0.num_composition_constraint_coeffs(), air0.trace_arguments()
             self._airs[key] = air0
         air = copy.copy(self._airs[key])
         air.public_inputs = stark.get_public_inputs()
