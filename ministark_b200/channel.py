@@ -87,6 +87,13 @@ class PublicCoin:
         return b
 
     def next_u64(self):
+        if not self.bytes:
+            self.counter += 1
+            self.bytes = merge_with_int(self.seed, self.counter)
+        if len(self.bytes) >= 8:        # eight pops from the end, first pop = most significant byte: the tail read little-endian
+            v = int.from_bytes(self.bytes[-8:], "little")
+            self.bytes = self.bytes[:-8]
+            return v
         return int.from_bytes(bytes(self._next_byte() for _ in range(8)), "big")
 
     def _draw_fp(self):
